@@ -1,0 +1,112 @@
+/*
+ * vit_b200.h -- C ABI of the B200-native batched HMM (Viterbi) decoder.
+ *
+ * Drop-in boundary for the ONE hot path of drwangxian/viterbi_spl: the float32 log-domain Viterbi recursion
+ *     delta_t[j] = max_i fl32(delta_{t-1}[i] + logA[i,j]) + logE_t[j]      (first maximum wins, as np.argmax)
+ * followed by the backtrace.  The reference has no FFI layer; what it would bind is
+ *   - the compiled numba module `viterbi_numba.core(B, prob_init, probs)`      dcnet/aot_viterbi_core.py:8-54,
+ *     called from `viterbi_numba_fn`                                            dcnet/tf_viterbi_decoding.py:119-153
+ *   - and the NumPy hot loops it duplicates 26 times, canonical form            imm/tf_viterbi.py:75-109.
+ * Every entry point below states which of those it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every buffer is owned by the caller (device buffers come from the caller's allocator,
+ *     e.g. torch); the library allocates no device memory and keeps no mutable global state except a launch
+ *     counter; it is re-entrant per stream and safe to use from one process per GPU.
+ *   - all pointers prefixed d_ are DEVICE pointers valid on the current CUDA device.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous on it.
+ *   - return value: VIT_OK (0) or a negative vit_status; nothing aborts or throws.
+ *   - inputs are LOG-domain float32 (the reference's prob-domain families take log(x + tiny) on the host with
+ *     NumPy before calling in, exactly where the reference takes it: dcnet/softmax_viterbi.py:2459-2465), so
+ *     paths are bit-identical to the reference's fp32 decode.  Values must be finite or -inf, never NaN.
+ */
+#ifndef VIT_B200_H_
+#define VIT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIT_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef enum vit_status {
+  VIT_OK = 0,
+  VIT_ERR_INVALID_ARGUMENT = -1, /* NULL pointer, B < 0, T_max < 1, S < 1 */
+  VIT_ERR_STATES_TOO_MANY = -2,  /* S > 65535: backpointers are uint16 */
+  VIT_ERR_WORKSPACE_TOO_SMALL = -3,
+  VIT_ERR_UNSUPPORTED_ALGO = -4, /* requested algorithm cannot run this shape on this device */
+  VIT_ERR_CUDA = -5,             /* a CUDA runtime call failed; see vit_last_cuda_error() */
+  VIT_ERR_MISALIGNED = -6        /* workspace pointer not 256-byte aligned */
+} vit_status;
+
+typedef enum vit_algo {
+  VIT_ALGO_AUTO = 0,
+  /* generic kernel: one CTA per clip, warp-shuffle (value,index) argmax, uint16 backpointer table in the
+   * workspace, one-thread-per-clip backtrace.  Any S <= 65535. */
+  VIT_ALGO_BACKPOINTER = 1,
+  /* persistent thread-block-cluster kernel: logA^T column-sharded and resident in shared memory, delta exchanged
+   * through distributed shared memory, register-tiled FADD2/FMNMX3 max-plus, delta history (fp32) in the workspace
+   * and the argmax resolved lazily by the backtrace only along the decoded path (bit-identical result). */
+  VIT_ALGO_CLUSTER = 2
+} vit_algo;
+
+/* Optional extras for vit_decode_f32_ex (all may be zero/NULL). */
+typedef struct vit_decode_opts {
+  int32_t algo;              /* vit_algo */
+  int32_t reserved;
+  uint16_t* d_backpointers;  /* [B][T_max][S] out: the reference's T2 table (row t=0 zero). Forces
+                                VIT_ALGO_BACKPOINTER. Replaces the int64 T2 of imm/tf_viterbi.py:92,99. */
+  float* d_delta;            /* [B][T_max][S] out: the reference's T1 table (imm/tf_viterbi.py:91,94,100). */
+} vit_decode_opts;
+
+/* Library version (VIT_B200_VERSION of the built library). */
+int vit_version(void);
+
+/* Static message for a vit_status. */
+const char* vit_strerror(int code);
+
+/* Text of the last CUDA error seen by this thread ("" if none). */
+const char* vit_last_cuda_error(void);
+
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t vit_launch_count(void);
+
+/* Which algorithm VIT_ALGO_AUTO resolves to for this shape on the current device (a vit_algo), or a negative
+ * vit_status. */
+int vit_select_algo(int B, int T_max, int S);
+
+/* Bytes of device workspace vit_decode_f32 needs for this shape and algorithm (algo may be VIT_ALGO_AUTO).
+ * The workspace holds what the reference keeps in its T1/T2 tables (imm/tf_viterbi.py:91-92): the uint16
+ * backpointer table or the fp32 delta history, plus the padded/sharded copy of logA^T. */
+int vit_workspace_bytes(int B, int T_max, int S, int algo, size_t* out_bytes);
+
+/*
+ * Batched decode.  Replaces viterbi_numba.core / viterbi_librosa_fn (imm/tf_viterbi.py:75-109) for B independent
+ * clips at once (the reference decodes one recording per call, dcnet/softmax_viterbi.py:3033-3040).
+ *
+ *   d_logA_T   [S][S]  dst-major: d_logA_T[j*S + i] = log A[i -> j]     (the reference's `B`,  imm/tf_viterbi.py:77)
+ *   d_log_pi   [S]                                                      (`log_prob_init`,       :82)
+ *   d_log_emis [B][T_max][S] row-major                                  (`probs` after the transpose at :89)
+ *   d_lengths  [B] int32 frames per clip, each in [0, T_max]; NULL = all T_max
+ *   d_paths    [B][T_max] int64 out (`states`, :102-107); frames >= length are set to -1
+ *   d_scores   [B] float32 out, max_j delta_{T-1}[j] (the value whose argmax :103 takes); may be NULL;
+ *              -inf for a zero-length clip
+ */
+int vit_decode_f32(const float* d_logA_T, const float* d_log_pi, const float* d_log_emis,
+                   const int32_t* d_lengths, int B, int T_max, int S,
+                   void* d_workspace, size_t workspace_bytes,
+                   int64_t* d_paths, float* d_scores, void* stream);
+
+/* Same, with an explicit algorithm and optional T1/T2 table outputs. */
+int vit_decode_f32_ex(const float* d_logA_T, const float* d_log_pi, const float* d_log_emis,
+                      const int32_t* d_lengths, int B, int T_max, int S,
+                      void* d_workspace, size_t workspace_bytes,
+                      int64_t* d_paths, float* d_scores, const vit_decode_opts* opts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIT_B200_H_ */

@@ -1,0 +1,78 @@
+"""ctypes binding of libvit_b200.so -- the C ABI declared in include/vit_b200.h.
+
+There is NO CPU fallback: if the CUDA library is missing or fails to load, importing the decoder raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libvit_b200.so')
+
+VIT_OK = 0
+ALGO_AUTO, ALGO_BACKPOINTER, ALGO_CLUSTER = 0, 1, 2
+ALGO_NAMES = {'auto': ALGO_AUTO, 'backpointer': ALGO_BACKPOINTER, 'cluster': ALGO_CLUSTER}
+
+# every symbol include/vit_b200.h declares (tests/test_abi.py checks the built library exports them all)
+EXPORTS = ['vit_version', 'vit_strerror', 'vit_last_cuda_error', 'vit_launch_count', 'vit_select_algo',
+           'vit_workspace_bytes', 'vit_decode_f32', 'vit_decode_f32_ex']
+
+
+class DecodeOpts(ctypes.Structure):
+    """struct vit_decode_opts"""
+    _fields_ = [('algo', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('d_backpointers', ctypes.c_void_p), ('d_delta', ctypes.c_void_p)]
+
+
+class VitError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f'libvit_b200: {msg} (status {code})')
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library (building is the job of viterbi_spl_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f'{LIB_PATH} not found: build it with `python -m viterbi_spl_b200.build` '
+                          '(needs nvcc; there is no CPU fallback)')
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    L.vit_version.restype = ci
+    L.vit_strerror.restype = ctypes.c_char_p
+    L.vit_strerror.argtypes = [ci]
+    L.vit_last_cuda_error.restype = ctypes.c_char_p
+    L.vit_launch_count.restype = ctypes.c_uint64
+    L.vit_select_algo.restype = ci
+    L.vit_select_algo.argtypes = [ci, ci, ci]
+    L.vit_workspace_bytes.restype = ci
+    L.vit_workspace_bytes.argtypes = [ci, ci, ci, ci, ctypes.POINTER(sz)]
+    L.vit_decode_f32.restype = ci
+    L.vit_decode_f32.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp, vp, vp]
+    L.vit_decode_f32_ex.restype = ci
+    L.vit_decode_f32_ex.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp, vp, ctypes.POINTER(DecodeOpts), vp]
+    _lib = L
+    return L
+
+
+def check(code):
+    if code != VIT_OK:
+        L = load()
+        msg = L.vit_strerror(code).decode()
+        if code == -5:
+            msg += ' [' + L.vit_last_cuda_error().decode() + ']'
+        raise VitError(code, msg)
+
+
+def workspace_bytes(B, T_max, S, algo=ALGO_AUTO):
+    out = ctypes.c_size_t(0)
+    check(load().vit_workspace_bytes(int(B), int(T_max), int(S), int(algo), ctypes.byref(out)))
+    return int(out.value)
+
+
+def launch_count():
+    return int(load().vit_launch_count())

@@ -1,0 +1,54 @@
+"""Builds libvit_b200.so (the CUDA decoder behind include/vit_b200.h) in-tree with nvcc for sm_100a.
+
+    python -m viterbi_spl_b200.build [--force]
+
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels with the repository snapshot to the GPU box.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libvit_b200.so')
+SOURCES = ['vit_api.cu', 'vit_backpointer.cu', 'vit_cluster.cu']
+HEADERS = ['vit_common.cuh', os.path.join('..', '..', 'include', 'vit_b200.h')]
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+              '--compiler-options', '-fPIC', '-shared', '-Xptxas', '-v']
+
+
+def nvcc():
+    exe = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(exe):
+        raise RuntimeError('nvcc not found: the CUDA decoder cannot be built')
+    return exe
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source into one shared library; returns its path."""
+    if not force and not stale():
+        return LIB
+    cmd = [nvcc()] + NVCC_FLAGS + ['-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    env = dict(os.environ)
+    env.pop('CC', None)   # the image exports a wrapper CC that nvcc must not pick up as host compiler
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout + res.stderr)
+    with open(os.path.join(HERE, 'build_ptxas.log'), 'w') as fh:
+        fh.write(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose=True))

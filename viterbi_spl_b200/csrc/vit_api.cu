@@ -1,0 +1,117 @@
+// extern "C" surface of libvit_b200.so (declared in include/vit_b200.h).
+#include <atomic>
+#include <cstring>
+#include <string>
+
+#include "vit_common.cuh"
+
+namespace vit {
+
+static std::atomic<uint64_t> g_launches{0};
+static thread_local std::string t_last_cuda_error;
+
+void note_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int cuda_fail(cudaError_t e) {
+  t_last_cuda_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e);
+  cudaGetLastError();   // clear the sticky-free error state
+  return VIT_ERR_CUDA;
+}
+
+// vit_backpointer.cu
+size_t bp_workspace_bytes(int B, int T_max, int S, bool external_bp);
+int bp_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
+              int T_max, int S, void* workspace, size_t workspace_bytes, int64_t* paths, float* scores,
+              uint16_t* bp_out, float* delta_out, cudaStream_t stream);
+// vit_cluster.cu
+size_t cluster_workspace_bytes(int B, int T_max, int S);
+bool cluster_supported(int S);
+int cluster_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
+                   int T_max, int S, void* workspace, size_t workspace_bytes, int64_t* paths, float* scores,
+                   float* delta_out, cudaStream_t stream);
+
+static int check_shape(int B, int T_max, int S) {
+  if (B < 0 || T_max < 1 || S < 1) return VIT_ERR_INVALID_ARGUMENT;
+  if (S > 65535) return VIT_ERR_STATES_TOO_MANY;
+  return VIT_OK;
+}
+
+static int resolve_algo(int algo, int S, bool want_bp) {
+  if (want_bp) return VIT_ALGO_BACKPOINTER;
+  if (algo == VIT_ALGO_AUTO) return cluster_supported(S) ? VIT_ALGO_CLUSTER : VIT_ALGO_BACKPOINTER;
+  if (algo == VIT_ALGO_BACKPOINTER) return algo;
+  if (algo == VIT_ALGO_CLUSTER) return cluster_supported(S) ? algo : VIT_ERR_UNSUPPORTED_ALGO;
+  return VIT_ERR_INVALID_ARGUMENT;
+}
+
+}  // namespace vit
+
+using namespace vit;
+
+extern "C" {
+
+int vit_version(void) { return VIT_B200_VERSION; }
+
+const char* vit_strerror(int code) {
+  switch (code) {
+    case VIT_OK: return "ok";
+    case VIT_ERR_INVALID_ARGUMENT: return "invalid argument (null pointer or non-positive size)";
+    case VIT_ERR_STATES_TOO_MANY: return "too many states: S must be <= 65535 (uint16 backpointers)";
+    case VIT_ERR_WORKSPACE_TOO_SMALL: return "workspace too small: query vit_workspace_bytes()";
+    case VIT_ERR_UNSUPPORTED_ALGO: return "requested algorithm does not support this shape on this device";
+    case VIT_ERR_CUDA: return "CUDA runtime error: see vit_last_cuda_error()";
+    case VIT_ERR_MISALIGNED: return "workspace pointer must be 256-byte aligned";
+    default: return "unknown vit_status";
+  }
+}
+
+const char* vit_last_cuda_error(void) { return t_last_cuda_error.c_str(); }
+
+uint64_t vit_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int vit_select_algo(int B, int T_max, int S) {
+  int rc = check_shape(B, T_max, S);
+  if (rc != VIT_OK) return rc;
+  return resolve_algo(VIT_ALGO_AUTO, S, false);
+}
+
+int vit_workspace_bytes(int B, int T_max, int S, int algo, size_t* out_bytes) {
+  if (!out_bytes) return VIT_ERR_INVALID_ARGUMENT;
+  int rc = check_shape(B, T_max, S);
+  if (rc != VIT_OK) return rc;
+  int a = resolve_algo(algo, S, false);
+  if (a < 0) return a;
+  *out_bytes = (a == VIT_ALGO_CLUSTER) ? cluster_workspace_bytes(B, T_max, S) : bp_workspace_bytes(B, T_max, S, false);
+  return VIT_OK;
+}
+
+int vit_decode_f32_ex(const float* d_logA_T, const float* d_log_pi, const float* d_log_emis,
+                      const int32_t* d_lengths, int B, int T_max, int S, void* d_workspace, size_t workspace_bytes,
+                      int64_t* d_paths, float* d_scores, const vit_decode_opts* opts, void* stream) {
+  int rc = check_shape(B, T_max, S);
+  if (rc != VIT_OK) return rc;
+  if (!d_logA_T || !d_log_pi || !d_paths || (!d_log_emis && B > 0)) return VIT_ERR_INVALID_ARGUMENT;
+  if (!d_workspace && workspace_bytes > 0) return VIT_ERR_INVALID_ARGUMENT;
+  if (((uintptr_t)d_workspace & 255u) != 0) return VIT_ERR_MISALIGNED;
+  const int algo_req = opts ? opts->algo : VIT_ALGO_AUTO;
+  uint16_t* bp_out = opts ? opts->d_backpointers : nullptr;
+  float* delta_out = opts ? opts->d_delta : nullptr;
+  const int algo = resolve_algo(algo_req, S, bp_out != nullptr);
+  if (algo < 0) return algo;
+  if (!d_workspace) return VIT_ERR_WORKSPACE_TOO_SMALL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (algo == VIT_ALGO_CLUSTER)
+    return cluster_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes,
+                          d_paths, d_scores, delta_out, st);
+  return bp_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_paths,
+                   d_scores, bp_out, delta_out, st);
+}
+
+int vit_decode_f32(const float* d_logA_T, const float* d_log_pi, const float* d_log_emis, const int32_t* d_lengths,
+                   int B, int T_max, int S, void* d_workspace, size_t workspace_bytes, int64_t* d_paths,
+                   float* d_scores, void* stream) {
+  return vit_decode_f32_ex(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes,
+                           d_paths, d_scores, nullptr, stream);
+}
+
+}  // extern "C"

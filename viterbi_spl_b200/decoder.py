@@ -1,0 +1,134 @@
+"""Batched B200 Viterbi decoder: the host side above the C ABI (include/vit_b200.h).
+
+``decode_batch`` is the new batched entry point; the reference's own entry points
+(``viterbi_spl_b200.reference_api``) are thin B=1 wrappers over it.  PyTorch is used only for device memory,
+streams and pinned staging buffers; all compute happens in libvit_b200.so.
+
+Tensor layouts (north star): posteriors/emissions ``[B, T, S]`` (``[T, S]`` per clip -- the reference's ``probs`` after
+the transpose at imm/tf_viterbi.py:89), initial log-probabilities ``[S]``, transposed log transition matrix
+``[S, S]`` dst-major (the reference's ``B = log_transition_matrix_T``, imm/tf_viterbi.py:77) -> int64 state paths
+``[B, T]`` (frames past a clip's length are -1) and float32 path scores ``[B]``.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class ViterbiDecoder:
+    """Holds the HMM parameters on one GPU plus a reusable workspace; decodes batches of clips.
+
+    Parameters are LOG-domain float32, exactly the arrays the reference's decoder objects keep
+    (``log_transition_matrix_T`` / ``log_ini_probs``, tonet/softmax_priors.py:1708-1709, 1788-1823).
+    """
+
+    def __init__(self, log_transition_matrix_T, log_prob_init, device=None, algo='auto'):
+        if not torch.cuda.is_available():
+            raise RuntimeError('viterbi_spl_b200 needs a CUDA device (B200); there is no CPU fallback')
+        self.lib = _lib.load()
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        A = torch.as_tensor(np.asarray(log_transition_matrix_T) if not torch.is_tensor(log_transition_matrix_T)
+                            else log_transition_matrix_T)
+        pi = torch.as_tensor(np.asarray(log_prob_init) if not torch.is_tensor(log_prob_init) else log_prob_init)
+        assert A.dtype == torch.float32 and pi.dtype == torch.float32, 'log-domain parameters must be float32'
+        assert A.ndim == 2 and A.shape[0] == A.shape[1], 'log_transition_matrix_T must be [S, S]'
+        self.S = int(A.shape[0])
+        assert pi.shape == (self.S,), 'log_prob_init must be [S]'
+        assert not bool(torch.isnan(A).any()) and not bool(torch.isnan(pi).any()), 'parameters contain NaN'
+        self.logA_T = A.to(self.device).contiguous()
+        self.log_pi = pi.to(self.device).contiguous()
+        self.algo = _lib.ALGO_NAMES[algo] if isinstance(algo, str) else int(algo)
+        self._ws = None
+        self._pinned = {}
+
+    # ---- device path ---------------------------------------------------------------------------------------
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def decode_device(self, log_emis, lengths=None, paths=None, scores=None, want_tables=False, stream=None):
+        """log_emis: CUDA float32 [B, T, S] contiguous; lengths: CUDA int32 [B] or None.
+        Returns (paths int64 [B, T], scores float32 [B]) CUDA tensors (+ (T1 float32, T2 uint16) if want_tables).
+        Asynchronous on `stream` (default: torch's current stream)."""
+        assert log_emis.is_cuda and log_emis.dtype == torch.float32 and log_emis.is_contiguous()
+        B, T, S = log_emis.shape
+        assert S == self.S, f'emissions have {S} states, model has {self.S}'
+        if lengths is not None:
+            assert lengths.is_cuda and lengths.dtype == torch.int32 and lengths.shape == (B,)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream() if stream is None else stream
+            with torch.cuda.stream(st):
+                if paths is None:
+                    paths = torch.empty((B, T), dtype=torch.int64, device=self.device)
+                if scores is None:
+                    scores = torch.empty((B,), dtype=torch.float32, device=self.device)
+                algo = _lib.ALGO_BACKPOINTER if want_tables else self.algo
+                ws = self._workspace(_lib.workspace_bytes(B, T, S, algo))
+                opts = _lib.DecodeOpts(algo=algo)
+                T1 = T2 = None
+                if want_tables:
+                    T1 = torch.zeros((B, T, S), dtype=torch.float32, device=self.device)
+                    T2 = torch.zeros((B, T, S), dtype=torch.uint16, device=self.device)
+                    opts.d_delta = T1.data_ptr()
+                    opts.d_backpointers = T2.data_ptr()
+                rc = self.lib.vit_decode_f32_ex(_ptr(self.logA_T), _ptr(self.log_pi), _ptr(log_emis), _ptr(lengths),
+                                                B, T, S, _ptr(ws), ws.numel(), _ptr(paths), _ptr(scores),
+                                                ctypes.byref(opts), ctypes.c_void_p(st.cuda_stream))
+                _lib.check(rc)
+        if want_tables:
+            return paths, scores, T1, T2
+        return paths, scores
+
+    # ---- host path (what the reference-facing wrappers use) --------------------------------------------------
+    def _pinned_buf(self, key, shape, dtype):
+        n = int(np.prod(shape))
+        buf = self._pinned.get(key)
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = torch.empty(max(n, 1), dtype=dtype).pin_memory()
+            self._pinned[key] = buf
+        return buf[:n].view(*shape)
+
+    def decode_host(self, log_emis, lengths=None):
+        """log_emis: host float32 array [B, T, S] (NumPy or CPU tensor).  Copies host->device, decodes, copies the
+        paths and scores back; returns NumPy (paths int64 [B, T], scores float32 [B])."""
+        E = torch.as_tensor(log_emis)
+        assert E.dtype == torch.float32 and E.ndim == 3
+        B, T, S = E.shape
+        with torch.cuda.device(self.device):
+            if E.is_pinned() and E.is_contiguous():
+                src = E
+            else:
+                src = self._pinned_buf('emis', (B, T, S), torch.float32)
+                src.copy_(E)
+            dE = src.to(self.device, non_blocking=True)
+            dL = None
+            if lengths is not None:
+                dL = torch.as_tensor(np.asarray(lengths, np.int32)).to(self.device)
+            paths, scores = self.decode_device(dE, dL)
+            hp = self._pinned_buf('paths', (B, T), torch.int64)
+            hs = self._pinned_buf('scores', (B,), torch.float32)
+            hp.copy_(paths, non_blocking=True)
+            hs.copy_(scores, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return hp.numpy().copy(), hs.numpy().copy()
+
+    def decode(self, log_emis, lengths=None):
+        """Dispatch on where the emissions live: CUDA tensor -> CUDA tensors, host array -> NumPy arrays."""
+        if torch.is_tensor(log_emis) and log_emis.is_cuda:
+            return self.decode_device(log_emis, lengths)
+        return self.decode_host(log_emis, lengths)
+
+
+def decode_batch(log_emis, logA_T, log_pi, lengths=None, algo='auto'):
+    """One-shot batched decode: ``log_emis [B, T, S]``, ``logA_T [S, S]`` (dst-major), ``log_pi [S]``,
+    ``lengths [B]`` or None -> ``(paths int64 [B, T], scores float32 [B])``.  Inputs on the GPU give GPU outputs."""
+    device = log_emis.device if (torch.is_tensor(log_emis) and log_emis.is_cuda) else None
+    return ViterbiDecoder(logA_T, log_pi, device=device, algo=algo).decode(log_emis, lengths)
