@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the Viterbi hot path (BASELINE.json metric: Viterbi frames/sec, 1024 clips x 3000 frames x 361 states).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--clips B --frames T --states S]
+
+One "step" = one pass of the decoder (forward recursion + backtrace) over one batch of synthetic log-posteriors.
+`value`  : whole-job frames/s with the batch already resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same through the public host API (ViterbiDecoder.decode_host): pinned host emissions -> device, decode,
+           paths + scores -> host, every step.
+`roofline`: the forward kernel against the FP32 max-plus issue peak of BASELINE.md section 4 (cells/s), timed with
+           CUDA events recorded by the library around that kernel; `roofline_hbm` gives the same launch in GB/s.
+`cpu_baseline`: the NumPy restatement of the reference decode (oracle/np_oracle.py, the reference's own CPU path is
+           NumPy) on a bounded sample of the same workload over all host cores.
+Under torchrun every rank decodes its own batch of the same shape (clips are independent: weak scaling, no collective
+on the data path); rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'viterbi_frames_per_sec'
+UNIT = 'frames/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--clips', type=int, default=1024)
+    ap.add_argument('--frames', type=int, default=3000)
+    ap.add_argument('--states', type=int, default=361)
+    ap.add_argument('--algo', default='auto')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0, help='target wall time of the cpu_baseline sample')
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f'batched max-plus Viterbi: {a.clips} clips x {a.frames} frames x {a.states} states (tonet state set), dense transition'
+
+
+def hmm_for(S):
+    from viterbi_spl_b200 import hmm_params
+    name = {321: 'dcnet', 361: 'tonet', 722: 'jdc'}.get(S)
+    if name is None:
+        from viterbi_spl_b200 import synth
+        return synth.dyadic_hmm(S, seed=S)
+    A, pi = hmm_params.synthetic_hmm(name)
+    return hmm_params.log_params(A, pi)
+
+
+# ---- CPU arm: the reference's NumPy decode, all host cores ------------------------------------------------------
+
+def _cpu_worker(args):
+    """One process = one core: decode `n` clips of [T, S] with the NumPy restatement; returns frames decoded."""
+    seed, n, T, S = args
+    for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[k] = '1'
+    from oracle import np_oracle
+    from viterbi_spl_b200 import synth
+    logA_T, log_pi = hmm_for(S)
+    frames = 0
+    for i in range(n):
+        E = synth.dyadic((T, S), seed * 1000 + i)
+        np_oracle.viterbi_log_np(logA_T, log_pi, E)
+        frames += T
+    return frames
+
+
+def cpu_sample(T, S, clips_per_core, cores):
+    """Wall-clock frames/s of `cores` processes each decoding `clips_per_core` clips."""
+    import multiprocessing as mp
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(i, 0, T, S) for i in range(cores)])          # import + page-in, untimed
+        t0 = time.perf_counter()
+        frames = sum(pool.map(_cpu_worker, [(i, clips_per_core, T, S) for i in range(cores)]))
+        dt = time.perf_counter() - t0
+    return frames / dt, dt, frames
+
+
+def cpu_baseline(a):
+    cores = os.cpu_count() or 1
+    # one 3000 x 361 clip costs ~0.45 s of one core; size the sample to ~a.cpu_seconds of wall time
+    per_clip_s = 0.45 * (a.frames / 3000.0) * (a.states / 361.0) ** 2
+    clips_per_core = max(1, int(a.cpu_seconds / per_clip_s))
+    clips_per_core = min(clips_per_core, 24)
+    fps, dt, frames = cpu_sample(a.frames, a.states, clips_per_core, cores)
+    return {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'{cores * clips_per_core} clips x {a.frames} frames x {a.states} states, {clips_per_core} per core, '
+                      f'{dt:.1f} s wall; NumPy restatement of imm/tf_viterbi.py:75-109 (TensorFlow not installed; the '
+                      f'reference calls its NumPy path the faster one)'}
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU decode (NumPy port; /root/reference is Python and does not travel)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_clip_s = 0.45 * (a.frames / 3000.0) * (a.states / 361.0) ** 2
+    # every step decodes clips_per_core clips on each core; keep the whole run within a few minutes
+    budget = 150.0 / max(1, a.steps + a.warmup)
+    clips_per_core = max(1, min(8, int(budget / per_clip_s)))
+    import multiprocessing as mp
+    ctx = mp.get_context('fork')
+    times = []
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(i, 0, a.frames, a.states) for i in range(cores)])
+        for step in range(a.warmup + a.steps):
+            t0 = time.perf_counter()
+            frames = sum(pool.map(_cpu_worker, [(step * cores + i, clips_per_core, a.frames, a.states) for i in range(cores)]))
+            dt = time.perf_counter() - t0
+            if step >= a.warmup:
+                times.append(dt)
+    total = sum(times)
+    fps = frames * len(times) / total
+    sample = (f'{cores * clips_per_core} clips x {a.frames} frames x {a.states} states per step '
+              f'({clips_per_core} per core x {cores} processes)')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
+        'warmup': a.warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(a), 'clips': a.clips, 'frames': a.frames, 'states': a.states,
+                   'sample_per_step': sample},
+        'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- clocks sampler ---------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), f'--query-gpu={self.FIELDS}',
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.12)
+        self.proc.terminate()     # exact PID we started
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        inside = [l for (ts, l) in self.lines if t_begin <= ts <= t_end] or [l for (_, l) in self.lines]
+        for l in inside:
+            parts = [p.strip() for p in l.split(',')]
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ---- GPU arm ----------------------------------------------------------------------------------------------------
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from viterbi_spl_b200 import ViterbiDecoder, _lib, synth
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    # CPU baseline first (N=1 only): worker processes are forked before this process creates a CUDA context
+    cpu = cpu_baseline(a) if (world == 1 and not a.no_cpu) else None
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl ours needs a CUDA device (there is no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, T, S = a.clips, a.frames, a.states
+    logA_T, log_pi = hmm_for(S)
+    dec = ViterbiDecoder(logA_T, log_pi, device=dev, algo=a.algo)
+    emis = synth.device_dense_softmax(B, T, S, seed=1234 + rank, device=dev)      # 4.4 GB: far larger than the 126 MB L2
+    paths = torch.empty((B, T), dtype=torch.int64, device=dev)
+    scores = torch.empty((B,), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    # ---- device-resident throughput ("value") + forward-kernel time ("roofline") -----------------------------
+    for _ in range(a.warmup):
+        dec.decode_device(emis, None, paths, scores)
+    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.2)
+    barrier()
+    launches0 = _lib.launch_count()
+    t_begin = time.perf_counter()
+    e0.record(stream)
+    for k in range(a.steps):
+        dec.decode_device(emis, None, paths, scores, forward_events=fwd_ev[k])
+    e1.record(stream)
+    barrier()
+    t_end = time.perf_counter()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    total_ms = e0.elapsed_time(e1)
+    fwd_ms = statistics.mean(x.elapsed_time(y) for (x, y) in fwd_ev)
+    t = torch.tensor([total_ms, fwd_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, fwd_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / a.steps
+    frames_per_rank = B * T
+    value = world * frames_per_rank / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the host API ------------------------------------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        host = torch.empty((B, T, S), dtype=torch.float32).pin_memory()
+        host.copy_(emis)
+        e2e_steps = max(1, min(a.steps, 5))
+        for _ in range(1):
+            dec.decode_host(host)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            hp, hs = dec.decode_host(host)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * frames_per_rank * e2e_steps / float(tt[0]), 'unit': UNIT,
+               'h2d_bytes_per_step': int(world * B * T * S * 4), 'd2h_bytes_per_step': int(world * (B * T * 8 + B * 4)),
+               'steps': e2e_steps, 'api': 'ViterbiDecoder.decode_host (pinned host emissions in, NumPy paths+scores out)'}
+        del host
+
+    # ---- parity spot check of the timed configuration against the oracle (not timed) ------------------------------
+    parity = None
+    if rank == 0:
+        try:
+            from oracle import c_oracle
+            nchk = min(B, 4)
+            ref_p, ref_s = c_oracle.decode_batch_c(logA_T, log_pi, emis[:nchk].cpu().numpy())
+            parity = bool(np.array_equal(ref_p, paths[:nchk].cpu().numpy()) and
+                          np.array_equal(ref_s, scores[:nchk].cpu().numpy()))
+        except Exception as ex:   # the oracle is test infrastructure; its absence must not break the bench
+            parity = f'oracle unavailable: {ex}'
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline (forward kernel) ------------------------------------------------------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    sm_mhz_peak = float(peaks.get('sm_max_mhz', 1965.0))
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured' if peaks else 'fallback'
+    cells = float(B) * (T - 1) * S * S                      # cells = sum_b (T_b - 1) S^2, 1 add + 1 max each
+    cells_per_s = cells / (fwd_ms * 1e-3)
+    alu_peak = 148 * 64 * sm_mhz_peak * 1e6                 # N_SM x 128 lanes x f / 2 instr per cell
+    algo_bytes = float(B) * T * S * 8                       # emissions in (4 B) + delta history out (4 B) per state-frame
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'forward_traffic.json')) as fh:
+            traffic = json.load(fh).get('dram_bytes_per_launch')
+    except Exception:
+        pass
+    roofline = {'bound': 'fp32_alu', 'kernel': 'cluster_forward_kernel', 'achieved': cells_per_s / 1e12,
+                'peak': alu_peak / 1e12, 'unit': 'Tcell/s', 'frac': cells_per_s / alu_peak,
+                'peak_definition': f'148 SMs x 64 cells/clk (FADD+FMNMX, 2 issue slots per cell) x {sm_mhz_peak:.0f} MHz '
+                                   f'({peak_src} sm_max_mhz)',
+                'kernel_ms': fwd_ms, 'kernel_share_of_step': fwd_ms / ms_per_step, 'traffic': traffic}
+    roofline_hbm = {'bound': 'hbm', 'achieved': algo_bytes / (fwd_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                    'frac': algo_bytes / (fwd_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': traffic,
+                    'note': f'{peak_src} copy bandwidth; the kernel is FP32-issue bound, not HBM bound'}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(a), 'clips_per_gpu': B, 'frames': T, 'states': S,
+                   'algo': {0: 'auto', 1: 'backpointer', 2: 'cluster'}.get(dec.algo, str(dec.algo)),
+                   'l2': 'inputs (4.4 GB emissions per step) are far larger than the 126 MB L2',
+                   'parallelism': f'{world} x independent clip shards, no data-path collective'},
+        'roofline': roofline, 'roofline_hbm': roofline_hbm,
+        'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'parity_vs_oracle': parity,
+    }
+    if cpu is not None:
+        line['cpu_baseline'] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == '__main__':
+    main()

@@ -60,6 +60,8 @@ typedef struct vit_decode_opts {
   uint16_t* d_backpointers;  /* [B][T_max][S] out: the reference's T2 table (row t=0 zero). Forces
                                 VIT_ALGO_BACKPOINTER. Replaces the int64 T2 of imm/tf_viterbi.py:92,99. */
   float* d_delta;            /* [B][T_max][S] out: the reference's T1 table (imm/tf_viterbi.py:91,94,100). */
+  void* ev_forward_begin;    /* optional cudaEvent_t recorded on `stream` right before the forward (recursion) kernel */
+  void* ev_forward_end;      /* optional cudaEvent_t recorded right after it (bench.py times the kernel with these) */
 } vit_decode_opts;
 
 /* Library version (VIT_B200_VERSION of the built library). */

@@ -20,7 +20,8 @@ EXPORTS = ['vit_version', 'vit_strerror', 'vit_last_cuda_error', 'vit_launch_cou
 class DecodeOpts(ctypes.Structure):
     """struct vit_decode_opts"""
     _fields_ = [('algo', ctypes.c_int32), ('reserved', ctypes.c_int32),
-                ('d_backpointers', ctypes.c_void_p), ('d_delta', ctypes.c_void_p)]
+                ('d_backpointers', ctypes.c_void_p), ('d_delta', ctypes.c_void_p),
+                ('ev_forward_begin', ctypes.c_void_p), ('ev_forward_end', ctypes.c_void_p)]
 
 
 class VitError(RuntimeError):

@@ -22,13 +22,13 @@ int cuda_fail(cudaError_t e) {
 size_t bp_workspace_bytes(int B, int T_max, int S, bool external_bp);
 int bp_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
               int T_max, int S, void* workspace, size_t workspace_bytes, int64_t* paths, float* scores,
-              uint16_t* bp_out, float* delta_out, cudaStream_t stream);
+              uint16_t* bp_out, float* delta_out, cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t stream);
 // vit_cluster.cu
 size_t cluster_workspace_bytes(int B, int T_max, int S);
 bool cluster_supported(int S);
 int cluster_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
                    int T_max, int S, void* workspace, size_t workspace_bytes, int64_t* paths, float* scores,
-                   float* delta_out, cudaStream_t stream);
+                   float* delta_out, cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t stream);
 
 static int check_shape(int B, int T_max, int S) {
   if (B < 0 || T_max < 1 || S < 1) return VIT_ERR_INVALID_ARGUMENT;
@@ -100,11 +100,13 @@ int vit_decode_f32_ex(const float* d_logA_T, const float* d_log_pi, const float*
   if (algo < 0) return algo;
   if (!d_workspace) return VIT_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t ev0 = opts ? (cudaEvent_t)opts->ev_forward_begin : nullptr;
+  cudaEvent_t ev1 = opts ? (cudaEvent_t)opts->ev_forward_end : nullptr;
   if (algo == VIT_ALGO_CLUSTER)
     return cluster_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes,
-                          d_paths, d_scores, delta_out, st);
+                          d_paths, d_scores, delta_out, ev0, ev1, st);
   return bp_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_paths,
-                   d_scores, bp_out, delta_out, st);
+                   d_scores, bp_out, delta_out, ev0, ev1, st);
 }
 
 int vit_decode_f32(const float* d_logA_T, const float* d_log_pi, const float* d_log_emis, const int32_t* d_lengths,

@@ -153,7 +153,8 @@ static int launch_forward(const float* logA_T, const float* log_pi, const float*
 
 int bp_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths,
               int B, int T_max, int S, void* workspace, size_t workspace_bytes,
-              int64_t* paths, float* scores, uint16_t* bp_out, float* delta_out, cudaStream_t stream) {
+              int64_t* paths, float* scores, uint16_t* bp_out, float* delta_out, cudaEvent_t ev0, cudaEvent_t ev1,
+              cudaStream_t stream) {
   if (S > 65535) return VIT_ERR_STATES_TOO_MANY;
   if (workspace_bytes < bp_workspace_bytes(B, T_max, S, bp_out != nullptr)) return VIT_ERR_WORKSPACE_TOO_SMALL;
   if (B == 0) return VIT_OK;
@@ -167,6 +168,7 @@ int bp_decode(const float* logA_T, const float* log_pi, const float* log_emis, c
   VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   // share each logA^T row among MSEQ clips once there are enough clips to keep every SM busy anyway
   int rc;
+  if (ev0) VIT_CUDA_TRY(cudaEventRecord(ev0, stream));
   if (B >= 8 * num_sms && (size_t)2 * 8 * S * sizeof(float) <= 200 * 1024)
     rc = launch_forward<8>(logA_T, log_pi, log_emis, lengths, B, T_max, S, bp, delta_out, scores, last_state, stream);
   else if (B >= 2 * num_sms && (size_t)2 * 4 * S * sizeof(float) <= 200 * 1024)
@@ -174,6 +176,7 @@ int bp_decode(const float* logA_T, const float* log_pi, const float* log_emis, c
   else
     rc = launch_forward<1>(logA_T, log_pi, log_emis, lengths, B, T_max, S, bp, delta_out, scores, last_state, stream);
   if (rc != VIT_OK) return rc;
+  if (ev1) VIT_CUDA_TRY(cudaEventRecord(ev1, stream));
 
   bp_backtrace_kernel<<<(B + 127) / 128, 128, 0, stream>>>(bp, last_state, lengths, B, T_max, S, paths);
   note_launch();

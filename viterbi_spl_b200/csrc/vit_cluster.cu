@@ -365,7 +365,8 @@ bool cluster_supported(int S) {
 
 int cluster_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths,
                    int B, int T_max, int S, void* workspace, size_t workspace_bytes,
-                   int64_t* paths, float* scores, float* delta_out, cudaStream_t stream) {
+                   int64_t* paths, float* scores, float* delta_out, cudaEvent_t ev0, cudaEvent_t ev1,
+                   cudaStream_t stream) {
   ClusterPlan p;
   if (!make_plan(S, &p) || forward_smem_bytes(p) > 227 * 1024) return VIT_ERR_UNSUPPORTED_ALGO;
   if (workspace_bytes < cluster_workspace_bytes(B, T_max, S)) return VIT_ERR_WORKSPACE_TOO_SMALL;
@@ -406,8 +407,10 @@ int cluster_decode(const float* logA_T, const float* log_pi, const float* log_em
   const int sub_batches = (B + kMC - 1) / kMC;
   const int n_clusters = sub_batches < max_clusters ? sub_batches : max_clusters;
   cfg.gridDim = dim3(n_clusters * p.C);
+  if (ev0) VIT_CUDA_TRY(cudaEventRecord(ev0, stream));
   VIT_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, (const float*)packed, log_pi, log_emis, lengths, B, T_max, S, p, hist));
   note_launch();
+  if (ev1) VIT_CUDA_TRY(cudaEventRecord(ev1, stream));
 
   const int warps_per_block = 4;
   cluster_backtrace_kernel<<<(B + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(

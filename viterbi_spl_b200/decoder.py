@@ -54,10 +54,12 @@ class ViterbiDecoder:
             self._ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def decode_device(self, log_emis, lengths=None, paths=None, scores=None, want_tables=False, stream=None):
+    def decode_device(self, log_emis, lengths=None, paths=None, scores=None, want_tables=False, stream=None,
+                      forward_events=None):
         """log_emis: CUDA float32 [B, T, S] contiguous; lengths: CUDA int32 [B] or None.
         Returns (paths int64 [B, T], scores float32 [B]) CUDA tensors (+ (T1 float32, T2 uint16) if want_tables).
-        Asynchronous on `stream` (default: torch's current stream)."""
+        Asynchronous on `stream` (default: torch's current stream).  forward_events: optional pair of
+        torch.cuda.Event(enable_timing=True) recorded by the library around the forward kernel."""
         assert log_emis.is_cuda and log_emis.dtype == torch.float32 and log_emis.is_contiguous()
         B, T, S = log_emis.shape
         assert S == self.S, f'emissions have {S} states, model has {self.S}'
@@ -79,6 +81,12 @@ class ViterbiDecoder:
                     T2 = torch.zeros((B, T, S), dtype=torch.uint16, device=self.device)
                     opts.d_delta = T1.data_ptr()
                     opts.d_backpointers = T2.data_ptr()
+                if forward_events is not None:
+                    for ev in forward_events:   # torch creates the cudaEvent lazily on first record
+                        if ev.cuda_event == 0:
+                            ev.record(st)
+                    opts.ev_forward_begin = forward_events[0].cuda_event
+                    opts.ev_forward_end = forward_events[1].cuda_event
                 rc = self.lib.vit_decode_f32_ex(_ptr(self.logA_T), _ptr(self.log_pi), _ptr(log_emis), _ptr(lengths),
                                                 B, T, S, _ptr(ws), ws.numel(), _ptr(paths), _ptr(scores),
                                                 ctypes.byref(opts), ctypes.c_void_p(st.cuda_stream))
