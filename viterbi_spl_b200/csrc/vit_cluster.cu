@@ -16,6 +16,8 @@
 //     the backtrace kernel resolves argmax_i fl32(delta_{t-1}[i] + logA^T[s_t][i]) only for the ONE state per frame
 //     that lies on the decoded path (first maximum wins, exactly np.argmax) -- S work per frame instead of S^2,
 //     bit-identical to following the reference's T2 table (imm/tf_viterbi.py:99, :105-107).
+#include <cstdlib>
+
 #include "vit_common.cuh"
 
 namespace vit {
@@ -30,14 +32,17 @@ struct ClusterPlan {
 };
 
 // tile configuration of the forward kernel
-constexpr int kMB = 8;    // clips per thread tile
-constexpr int kNJ = 4;    // target states per thread tile
-constexpr int kKS = 4;    // K split across adjacent lanes
-constexpr int kBG = 4;    // clip groups per CTA  -> MC = 32 clips per cluster
-constexpr int kJG = 24;   // target groups per CTA -> up to 96 target states per CTA
-constexpr int kMC = kMB * kBG;
-constexpr int kThreads = kBG * kJG * kKS;   // 384
-constexpr int kMaxShard = kNJ * kJG;        // 96
+constexpr int kMB = 8;      // clips per thread tile
+constexpr int kNJ = 4;      // target states per thread tile
+constexpr int kKS = 4;      // K split across adjacent lanes
+constexpr int kJG = 24;     // target groups per CTA -> up to 96 target states per CTA
+constexpr int kBG = 2;      // clip groups per pipeline
+constexpr int kPipes = 2;   // independent pipelines (warp groups) per CTA, each decoding its own kMC clips
+constexpr int kMC = kMB * kBG;                    // 16 clips per pipeline (and per cluster-wide pipeline)
+constexpr int kPipeThreads = kBG * kJG * kKS;     // 192 threads = 6 warps per pipeline
+constexpr int kThreads = kPipes * kPipeThreads;   // 384
+constexpr int kMaxShard = kNJ * kJG;              // 96
+constexpr int kNOUT = kMB * kNJ / kKS;            // outputs finalised per thread per step
 
 static bool make_plan(int S, ClusterPlan* p) {
   int C = (S <= kMaxShard) ? 1 : (S <= 2 * kMaxShard ? 2 : 4);
@@ -56,7 +61,7 @@ static bool make_plan(int S, ClusterPlan* p) {
 }
 
 static size_t forward_smem_bytes(const ClusterPlan& p) {
-  return (size_t)(p.NCmax + 2 * kMC) * p.KP * sizeof(float) + 64;
+  return (size_t)(p.NCmax + kPipes * 2 * kMC) * p.KP * sizeof(float) + 64;
 }
 
 // Re-lays logA^T [S][S] (dst-major) as [C][NCmax][KP]: shard-major target rows, K positions grouped by shard with
@@ -81,20 +86,27 @@ __global__ void cluster_pack_logA_kernel(const float* __restrict__ logA_T, int S
   }
 }
 
-template <bool PACKED>
+__device__ __forceinline__ void pipe_bar_sync(int pipe) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + pipe), "n"(kPipeThreads) : "memory");
+}
+
+// KP_CT: compile-time padded K extent (0 = take it from the plan at run time); the hot shapes (S = 361 -> 368,
+// S = 321 -> 336) get immediate shared-memory offsets in the K loop.
+template <int KP_CT>
 __global__ void __launch_bounds__(kThreads, 1)
 cluster_forward_kernel(const float* __restrict__ packedA, const float* __restrict__ log_pi,
                        const float* __restrict__ log_emis, const int32_t* __restrict__ lengths,
-                       int B, int T_max, int S, ClusterPlan p, float* __restrict__ hist) {
-  constexpr int MB = kMB, NJ = kNJ, KS = kKS, JG = kJG, MC = kMC;
-  constexpr int NOUT = MB * NJ / KS;   // outputs finalised per thread
+                       int B, int T_max, int S, ClusterPlan p, float* __restrict__ hist, int dev) {
+  // dev: timing experiments only (results invalid): 1 = no HBM traffic, 2 = no delta exchange, 4 = no K loop
+  constexpr int MB = kMB, NJ = kNJ, KS = kKS, JG = kJG, MC = kMC, NOUT = kNOUT;
   extern __shared__ __align__(128) float smem[];
-  const int KP = p.KP, NCP = p.NCP;
+  const int KP = KP_CT ? KP_CT : p.KP;
   const int KP4 = KP / 4;
-  float* sA = smem;                                   // [NCmax][KP]
-  float* sD = sA + (size_t)p.NCmax * KP;              // [2][MC][KP]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(sD + (size_t)2 * MC * KP);   // [2]
-  __shared__ int s_len[MC];
+  const int NCP = p.NCP;
+  float* sA = smem;                                     // [NCmax][KP]             resident logA^T shard
+  float* sDall = sA + (size_t)p.NCmax * KP;             // [kPipes][2][MC][KP]     delta double buffers
+  uint64_t* s_bar_all = reinterpret_cast<uint64_t*>(sDall + (size_t)kPipes * 2 * MC * KP);   // [kPipes][2]
+  __shared__ int s_len_all[kPipes][MC];
 
   const int tid = threadIdx.x;
   const uint32_t C = cluster_nctarank();
@@ -107,21 +119,29 @@ cluster_forward_kernel(const float* __restrict__ packedA, const float* __restric
     const float4* src = reinterpret_cast<const float4*>(packedA + (size_t)rank * p.NCmax * KP);
     float4* dst = reinterpret_cast<float4*>(sA);
     for (int x = tid; x < p.NCmax * KP4; x += kThreads) dst[x] = src[x];
-    float4* d4 = reinterpret_cast<float4*>(sD);
+    float4* d4 = reinterpret_cast<float4*>(sDall);
     const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    for (int x = tid; x < 2 * MC * KP4; x += kThreads) d4[x] = ninf;
+    for (int x = tid; x < kPipes * 2 * MC * KP4; x += kThreads) d4[x] = ninf;
     if (tid == 0) {
-      mbar_init(smem_u32(&s_bar[0]), 1);
-      mbar_init(smem_u32(&s_bar[1]), 1);
+      for (int i = 0; i < kPipes * 2; ++i) mbar_init(smem_u32(&s_bar_all[i]), 1);
       mbar_fence_init();
     }
   }
   __syncthreads();
   if (C > 1) cluster_sync();   // every CTA's barriers and buffers exist before any peer copy can land
 
-  const int q = tid % KS;
-  const int jg = (tid / KS) % JG;
-  const int bg = tid / (KS * JG);
+  // ---- two independent pipelines per CTA: warps 0-5 and 6-11.  Each owns MC clips, its own delta buffers and
+  //      mbarriers, and is only ever synchronised with the SAME pipeline of the peer CTAs, so one pipeline's
+  //      reduce / store / exchange phase overlaps the other's K loop.
+  const int pipe = tid / kPipeThreads;
+  const int gt = tid - pipe * kPipeThreads;
+  float* sD = sDall + (size_t)pipe * 2 * MC * KP;
+  uint64_t* s_bar = s_bar_all + pipe * 2;
+  int* s_len = s_len_all[pipe];
+
+  const int q = gt % KS;
+  const int jg = (gt / KS) % JG;
+  const int bg = gt / (KS * JG);
   // logA^T row offsets (in float4) of this thread's NJ targets; out-of-shard targets alias the last row
   int a_off[NJ];
 #pragma unroll
@@ -129,63 +149,55 @@ cluster_forward_kernel(const float* __restrict__ packedA, const float* __restric
   const int nchunks = KP4 / KS;
   const uint32_t row_bytes = (uint32_t)NCP * sizeof(float);
   const uint32_t tx_bytes = (C - 1) * MC * row_bytes;
+  // after the recursive-halving reduction lane q holds flat outputs [8q, 8q+8): clips 2q, 2q+1 of its tile, all NJ
+  // targets
+  const int m0 = bg * MB + 2 * q;
+  bool o_valid[NJ];
+#pragma unroll
+  for (int n = 0; n < NJ; ++n) o_valid[n] = (jg + n * JG) < nc_mine;
 
-  uint32_t g = 0;   // global step counter: delta of step g lives in buffer g & 1, guarded by barrier g & 1
-  for (int sb = cluster_id_x(); sb * MC < B; sb += num_clusters_x()) {
+  uint32_t g = 0;   // pipeline step counter: delta of step g lives in buffer g & 1, guarded by barrier g & 1
+  for (int sb = (int)cluster_id_x() * kPipes + pipe; sb * MC < B; sb += (int)num_clusters_x() * kPipes) {
     const int seq0 = sb * MC;
-    if (tid < MC) {
-      const int b = seq0 + tid;
-      s_len[tid] = (b < B) ? (lengths ? lengths[b] : T_max) : 0;
+    if (gt < MC) {
+      const int b = seq0 + gt;
+      s_len[gt] = (b < B) ? (lengths ? lengths[b] : T_max) : 0;
     }
-    __syncthreads();
+    pipe_bar_sync(pipe);
     int maxlen = 0;
     for (int m = 0; m < MC; ++m) maxlen = max(maxlen, s_len[m]);
-
-    // this thread's NOUT outputs: flat = k*KS + q -> clip mb = flat / NJ of its group, target n = flat % NJ
-    int o_m[NOUT], o_j[NOUT], o_len[NOUT];
-    size_t o_off[NOUT];
-    bool o_valid[NOUT];
-#pragma unroll
-    for (int k = 0; k < NOUT; ++k) {
-      const int flat = k * KS + q;
-      const int m = bg * MB + flat / NJ;
-      const int jl = jg + (flat % NJ) * JG;
-      o_m[k] = m;
-      o_j[k] = jl;
-      o_len[k] = s_len[m];
-      o_valid[k] = jl < nc_mine;
-      o_off[k] = (size_t)(seq0 + m) * T_max * S + (j_start + jl);
-    }
+    const int len0 = s_len[m0], len1 = s_len[m0 + 1];
+    const size_t off0 = (size_t)(seq0 + m0) * T_max * S + (j_start + jg);
+    const size_t off1 = off0 + (size_t)T_max * S;
 
     for (int t = 0; t < maxlen; ++t, ++g) {
       const uint32_t buf = g & 1u;
       // emissions of this step for my outputs: issued first, consumed after the K loop          (hides HBM latency)
       float e[NOUT];
 #pragma unroll
-      for (int k = 0; k < NOUT; ++k)
-        e[k] = (o_valid[k] && t < o_len[k]) ? ld_global_nc_f32(log_emis + o_off[k] + (size_t)t * S) : 0.f;
+      for (int k = 0; k < NOUT; ++k) {
+        const int n = k % NJ;
+        const bool live = o_valid[n] && t < (k < NJ ? len0 : len1) && !(dev & 1);
+        e[k] = live ? ld_global_nc_f32(log_emis + (k < NJ ? off0 : off1) + (size_t)t * S + n * JG) : 0.f;
+      }
 
-      float acc[MB][NJ];
+      float acc[MB * NJ];
       if (t == 0) {
         // T1[0] = log_pi + logE[0]                                                              (imm/tf_viterbi.py:94)
 #pragma unroll
-        for (int b = 0; b < MB; ++b)
-#pragma unroll
-          for (int n = 0; n < NJ; ++n) {
-            const int jl = jg + n * JG;
-            acc[b][n] = (jl < nc_mine) ? log_pi[j_start + jl] : -INFINITY;
-          }
+        for (int k = 0; k < NOUT; ++k) {
+          const int n = k % NJ;
+          acc[k] = o_valid[n] ? log_pi[j_start + jg + n * JG] : -INFINITY;
+        }
       } else {
         // delta_{t-1} from the peers has landed in buffer (g-1)&1 ?
-        if (C > 1) mbar_wait(smem_u32(&s_bar[buf ^ 1u]), ((g - 1) >> 1) & 1u);
+        if (C > 1 && !(dev & 2)) mbar_wait(smem_u32(&s_bar[buf ^ 1u]), ((g - 1) >> 1) & 1u);
 #pragma unroll
-        for (int b = 0; b < MB; ++b)
-#pragma unroll
-          for (int n = 0; n < NJ; ++n) acc[b][n] = -INFINITY;
+        for (int i = 0; i < MB * NJ; ++i) acc[i] = -INFINITY;
         const float4* pD = reinterpret_cast<const float4*>(sD + (size_t)(buf ^ 1u) * MC * KP) + (bg * MB) * KP4 + q;
         const float4* pA = reinterpret_cast<const float4*>(sA);
 #pragma unroll 2
-        for (int c = 0; c < nchunks; ++c) {
+        for (int c = 0; c < ((dev & 4) ? 1 : nchunks); ++c) {
           float4 d[MB], a[NJ];
 #pragma unroll
           for (int b = 0; b < MB; ++b) d[b] = pD[b * KP4 + c * KS];
@@ -195,70 +207,67 @@ cluster_forward_kernel(const float* __restrict__ packedA, const float* __restric
           for (int b = 0; b < MB; ++b)
 #pragma unroll
             for (int n = 0; n < NJ; ++n) {
-              // Bt[j, i] = T1[t-1][i] + B[j, i]; running max over i                              (:98-99, value part)
-              if (PACKED) {
-                float v0, v1, v2, v3;
-                fadd2(v0, v1, d[b].x, d[b].y, a[n].x, a[n].y);
-                fadd2(v2, v3, d[b].z, d[b].w, a[n].z, a[n].w);
-                acc[b][n] = fmax3(acc[b][n], v0, v1);
-                acc[b][n] = fmax3(acc[b][n], v2, v3);
-              } else {
-                acc[b][n] = fmaxf(acc[b][n], __fadd_rn(d[b].x, a[n].x));
-                acc[b][n] = fmaxf(acc[b][n], __fadd_rn(d[b].y, a[n].y));
-                acc[b][n] = fmaxf(acc[b][n], __fadd_rn(d[b].z, a[n].z));
-                acc[b][n] = fmaxf(acc[b][n], __fadd_rn(d[b].w, a[n].w));
-              }
+              // Bt[j, i] = T1[t-1][i] + B[j, i]; running max over i                       (:98-99, value part).
+              // ptxas fuses each pair of maxes into one FMNMX3; the adds stay scalar FADD.
+              float m = acc[b * NJ + n];
+              m = fmaxf(m, __fadd_rn(d[b].x, a[n].x));
+              m = fmaxf(m, __fadd_rn(d[b].y, a[n].y));
+              m = fmaxf(m, __fadd_rn(d[b].z, a[n].z));
+              m = fmaxf(m, __fadd_rn(d[b].w, a[n].w));
+              acc[b * NJ + n] = m;
             }
         }
-        // combine the KS partial maxima (adjacent lanes)
+        // combine the KS partial maxima by recursive halving over the KS adjacent lanes: each round a lane keeps one
+        // half of its values, sends the other half to its partner and folds in what it receives
+        int len = MB * NJ;
 #pragma unroll
-        for (int b = 0; b < MB; ++b)
+        for (int off = KS / 2; off >= 1; off >>= 1) {
+          const bool upper = (q & off) != 0;
+          len >>= 1;
 #pragma unroll
-          for (int n = 0; n < NJ; ++n)
-#pragma unroll
-            for (int off = 1; off < KS; off <<= 1)
-              acc[b][n] = fmaxf(acc[b][n], __shfl_xor_sync(0xffffffffu, acc[b][n], off));
+          for (int i = 0; i < MB * NJ / 2; ++i) {
+            if (i < len) {
+              const float keep = upper ? acc[i + len] : acc[i];
+              const float send = upper ? acc[i] : acc[i + len];
+              acc[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+            }
+          }
+        }
       }
 
       // T1[t][j] = max + logE[t][j]                                                              (:100)
-      float outv[NOUT];
-#pragma unroll
-      for (int b = 0; b < MB; ++b)
-#pragma unroll
-        for (int n = 0; n < NJ; ++n)
-          if (((b * NJ + n) % KS) == q) outv[(b * NJ + n) / KS] = acc[b][n];
       float* sDn = sD + (size_t)buf * MC * KP + (size_t)rank * NCP;
 #pragma unroll
       for (int k = 0; k < NOUT; ++k) {
-        if (o_valid[k]) {
-          const float v = __fadd_rn(outv[k], e[k]);
-          sDn[o_m[k] * KP + o_j[k]] = v;
-          if (t < o_len[k]) st_global_cs_f32(hist + o_off[k] + (size_t)t * S, v);
+        const int n = k % NJ;
+        if (o_valid[n]) {
+          const float v = __fadd_rn(acc[k], e[k]);
+          sDn[(m0 + k / NJ) * KP + jg + n * JG] = v;
+          if (t < (k < NJ ? len0 : len1) && !(dev & 1))
+            st_global_cs_f32(hist + (k < NJ ? off0 : off1) + (size_t)t * S + n * JG, v);
         }
       }
-      if (C > 1) {
+      if (C > 1 && !(dev & 2)) {
         fence_proxy_async_smem();
-        __syncthreads();
-        // all-gather: my [MC][NCP] slice of delta_t -> the same place in every peer's buffer
-        if (tid == 0) mbar_arrive_expect_tx(smem_u32(&s_bar[buf]), tx_bytes);
-        if (tid < (int)(C - 1) * MC) {
-          const int m = tid % MC;
-          const uint32_t peer = (rank + 1 + tid / MC) % C;
+        pipe_bar_sync(pipe);
+        // all-gather: my [MC][NCP] slice of delta_t -> the same place in the same pipeline's buffer of every peer
+        if (gt == 0) mbar_arrive_expect_tx(smem_u32(&s_bar[buf]), tx_bytes);
+        if (gt < (int)(C - 1) * MC) {
+          const int m = gt % MC;
+          const uint32_t peer = (rank + 1 + gt / MC) % C;
           const uint32_t src = smem_u32(sDn + m * KP);
           dsmem_bulk_copy(mapa(src, peer), src, row_bytes, mapa(smem_u32(&s_bar[buf]), peer));
         }
       } else {
-        __syncthreads();
+        pipe_bar_sync(pipe);
       }
     }
-    if (C > 1) {
-      // drain the last step's exchange, then make sure no peer still reads a buffer the next sub-batch overwrites
-      if (maxlen > 0) mbar_wait(smem_u32(&s_bar[(g - 1) & 1u]), ((g - 1) >> 1) & 1u);
-      cluster_sync();
-    } else {
-      __syncthreads();
-    }
+    // drain the last step's exchange.  Once it has completed, every peer has finished the K loop of its last step, so
+    // none of them still reads the buffer that step 0 of this pipeline's next sub-batch will overwrite.
+    if (C > 1 && maxlen > 0 && !(dev & 2)) mbar_wait(smem_u32(&s_bar[(g - 1) & 1u]), ((g - 1) >> 1) & 1u);
+    pipe_bar_sync(pipe);   // s_len is rewritten next
   }
+  __syncthreads();
   if (C > 1) cluster_sync();   // no CTA may exit while peers can still address its shared memory
 }
 
@@ -384,7 +393,11 @@ int cluster_decode(const float* logA_T, const float* log_pi, const float* log_em
     VIT_CUDA_TRY(cudaGetLastError());
   }
 
-  auto kern = cluster_forward_kernel<true>;
+  const char* dev_s = getenv("VIT_DEV_FLAGS");
+  const int dev = dev_s ? atoi(dev_s) : 0;
+  auto kern = cluster_forward_kernel<0>;
+  if (p.KP == 368) kern = cluster_forward_kernel<368>;        // S = 361 (tonet)
+  else if (p.KP == 336) kern = cluster_forward_kernel<336>;   // S = 321 (dcnet / msnet / ftanet)
   const size_t smem = forward_smem_bytes(p);
   VIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
@@ -404,11 +417,12 @@ int cluster_decode(const float* logA_T, const float* log_pi, const float* log_em
   cfg.gridDim = dim3(p.C);
   VIT_CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
   if (max_clusters < 1) return VIT_ERR_UNSUPPORTED_ALGO;
-  const int sub_batches = (B + kMC - 1) / kMC;
-  const int n_clusters = sub_batches < max_clusters ? sub_batches : max_clusters;
+  const int sub_batches = (B + kMC - 1) / kMC;                       // one per pipeline
+  const int want = (sub_batches + kPipes - 1) / kPipes;
+  const int n_clusters = want < max_clusters ? want : max_clusters;
   cfg.gridDim = dim3(n_clusters * p.C);
   if (ev0) VIT_CUDA_TRY(cudaEventRecord(ev0, stream));
-  VIT_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, (const float*)packed, log_pi, log_emis, lengths, B, T_max, S, p, hist));
+  VIT_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, (const float*)packed, log_pi, log_emis, lengths, B, T_max, S, p, hist, dev));
   note_launch();
   if (ev1) VIT_CUDA_TRY(cudaEventRecord(ev1, stream));
 
