@@ -159,3 +159,51 @@ def imm_viterbi_class():
 
 def imm_gen_transition_matrix():
     return ref_toplevel('imm/transition_matrix.py', 'gen_transition_matrix_fn')
+
+
+def run_ref_script(relpath, files):
+    """Execute one of the reference's top-level parameter scripts (e.g. dcnet/viterbi_transition_matrix.py) in a temp
+    directory holding the given input arrays as `<name>.dat`, with stub modules for its TensorFlow/plotting imports.
+    Returns {record name: array} for every .dat the script wrote."""
+    import contextlib
+    import io
+    import runpy
+    import sys
+    import tempfile
+    import types
+
+    saver, loader = dat_saver(), dat_loader()
+    sd = types.ModuleType('self_defined')
+    sd.load_np_array_from_file_fn = loader
+    sd.save_np_array_to_file_fn = saver
+
+    class _Any(types.ModuleType):
+        def __getattr__(self, k):
+            return lambda *a, **kw: None
+
+    stubs = {'self_defined': sd}
+    for m in ['librosa', 'matplotlib', 'matplotlib.pyplot', 'scipy.stats']:
+        stubs[m] = _Any(m)
+    stubs['matplotlib'].pyplot = stubs['matplotlib.pyplot']
+    old = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    cwd = os.getcwd()
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            for name, arr in files.items():
+                saver(name + '.dat', arr, name)
+            with contextlib.redirect_stdout(io.StringIO()):
+                runpy.run_path(os.path.join(REF_ROOT, relpath), run_name='__main__')
+            for f in os.listdir(d):
+                if f.endswith('.dat') and f[:-4] not in files:
+                    out[f[:-4]] = loader(f)[1]
+        finally:
+            os.chdir(cwd)
+            for k, v in old.items():
+                if v is None:
+                    sys.modules.pop(k, None)
+                else:
+                    sys.modules[k] = v
+    return out

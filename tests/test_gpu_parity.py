@@ -1,0 +1,293 @@
+"""Parity tests proper (run on the B200 with `-m gpu`): the CUDA decoders, called through the C ABI, against
+
+  * the golden vectors produced by executing the reference's own functions (tests/golden/make_golden.py),
+  * the CPU oracle on the same seeded inputs (sizes the oracle finishes in seconds),
+  * size-independent properties at BASELINE.json's full size (1024 clips x 3000 frames x 361 states).
+
+Bar: bit-exact state paths AND bit-exact fp32 path scores (the north star asks 1e-5 relative on scores; the
+arithmetic is the same sequence of binary32 adds, so equality is what is asserted).
+"""
+import ctypes
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, np_oracle
+from viterbi_spl_b200 import hmm_params, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+ALGOS = ['cluster', 'backpointer']
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def sha(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+@pytest.fixture(scope='module')
+def Decoder(cuda_lib):
+    assert torch.cuda.is_available(), 'gpu-marked tests need a CUDA device'
+    from viterbi_spl_b200 import ViterbiDecoder
+    return ViterbiDecoder
+
+
+def algos_for(S):
+    return ALGOS if S <= 364 else ['backpointer', 'auto']
+
+
+# ---- golden vectors (made by the reference's own code) ------------------------------------------------------------
+
+@pytest.mark.parametrize('tag', ['dyadic361', 'ties361', 'dyadic722', 'ties97', 't1', 't2'])
+def test_golden_exact_inputs(Decoder, tag):
+    g = load('exact_inputs.npz')
+    S, T, coarse = (int(x) for x in g[tag + '_spec'])
+    A, pi = synth.dyadic_hmm(S, seed=S + T, coarse=bool(coarse))
+    E = synth.tie_stress((T, S), seed=7 * S + T) if coarse else synth.dyadic((T, S), seed=7 * S + T)
+    assert sha(A, pi, E) == str(g[tag + '_sha'])
+    for algo in algos_for(S):
+        paths, scores = Decoder(A, pi, algo=algo).decode_host(E[None])
+        assert paths.dtype == np.int64 and np.array_equal(paths[0], g[tag + '_states']), (tag, algo)
+
+
+@pytest.mark.parametrize('algo', ALGOS)
+def test_golden_msnet_shipped_parameters(Decoder, algo):
+    g = load('msnet_logdomain.npz')
+    dec = Decoder(g['logA_T'], g['log_pi'], algo=algo)
+    E = np.stack([g['E_dense'], g['E_sparse']])
+    paths, scores = dec.decode_host(E)
+    assert np.array_equal(paths[0], g['states_dense'])
+    assert np.array_equal(paths[1], g['states_sparse'])
+    m = load('msnet_softmax_viterbi.npz')
+    for scaled in (0, 1):
+        st = dec.decode_host(m[f'log_prob_ts_{scaled}'][None])[0][0]
+        assert np.array_equal(st < 320, m[f'voiced_{scaled}'])
+        assert np.array_equal(np.minimum(st, 319), m[f'bins_{scaled}'])
+
+
+def test_golden_imm_dense_matrix(Decoder):
+    g = load('imm_dense.npz')
+    A = hmm_params.dense_imm_transition_matrix(20, 721)
+    logA_T, log_pi = hmm_params.log_params(A, np.full([722], 1. / 722), add_tiny=False)
+    if sha(logA_T) != str(g['logA_T_sha']):
+        pytest.skip('float64 log of this machine differs from the golden generator')
+    E = np.require(g['log_HF0'].T, requirements=['C'])
+    paths, _ = Decoder(logA_T, log_pi).decode_host(E[None])
+    assert np.array_equal(paths[0], g['states'])
+
+
+# ---- the reference's entry points (families A-D) --------------------------------------------------------------------
+
+def test_reference_entry_points(Decoder):
+    from viterbi_spl_b200 import reference_api as api
+    tiny = np.finfo(np.float32).tiny
+    g = load('family_a.npz')
+    same_libm = np.array_equal(np.log(g['probs_st'].T + tiny), g['log_probs_ts'])
+    want = g['states'] if same_libm else np_oracle.family_a_np(transition_matrix=g['A'], prob_init=g['pi'], probs_st=g['probs_st'])
+    probs_f = np.asfortranarray(g['probs_st'])
+    keep = probs_f.copy(order='F')
+    for fn in (api.Viterbi.viterbi_librosa_fn, api.viterbi_librosa_c_fn):
+        got = fn(transition_matrix=g['A'], prob_init=g['pi'], probs_st=probs_f)
+        assert got.dtype == np.int64 and np.array_equal(got, want)
+        assert np.array_equal(probs_f, keep)                               # Family A does not mutate its inputs
+    assert np.array_equal(api.viterbi_tf_fn(g['A'], g['pi'], g['probs_st']), want.astype(np.int32))
+    # numba path: the core logs its inputs in place; an F-ordered probs_st is reached through the view
+    p2 = probs_f.copy(order='F')
+    got = api.viterbi_numba_fn(transition_matrix=g['A'], prob_init=g['pi'], probs_st=p2)
+    assert np.array_equal(got, want)
+    assert np.array_equal(p2, np.log(keep + tiny))
+    # log-domain function
+    got = api.viterbi_librosa_fn(log_transition_matrix_T=g['logA_T'], log_prob_init=g['log_pi'],
+                                 log_probs_st=np.require(g['log_probs_ts'].T, requirements=['C']))
+    assert np.array_equal(got, g['states'])
+
+    # Family B (tonet): F-ordered prob-domain [S, T], logged in place
+    b = load('tonet_family_b.npz')
+    vb = api.ViterbiB(b['A'], b['pi'])
+    assert np.array_equal(vb.log_transition_matrix_T, b['logA_T']) or not same_libm
+    probs = np.asfortranarray(b['probs_st'])
+    want_b = b['states'] if np.array_equal(np.log(b['probs_st'] + tiny), b['log_probs_st']) else \
+        np_oracle.viterbi_log_np(vb.log_transition_matrix_T, vb.log_ini_probs, np.log(b['probs_st'].T + tiny))[0]
+    got = vb.viterbi_librosa_fn(probs)
+    assert np.array_equal(got, want_b)
+    assert np.array_equal(probs, np.log(b['probs_st'] + tiny))             # mutated in place like the reference
+    with pytest.raises(AssertionError):
+        vb.viterbi_librosa_fn(np.ascontiguousarray(b['probs_st']))         # must be F-contiguous
+    voiced, bins = api.voiced_and_bins(got, 360)
+    if want_b is b['states']:
+        assert np.array_equal(voiced, b['voiced']) and np.array_equal(bins, b['bins'])
+
+    # Family C (msnet shipped parameters): C-ordered prob-domain [T, S]
+    m = load('msnet_softmax_viterbi.npz')
+    ml = load('msnet_logdomain.npz')
+    A_lin = np.exp(ml['logA_T'].T.astype(np.float64)).astype(np.float32)
+    A_lin[ml['logA_T'].T < -80] = 0
+    A_lin = (A_lin / A_lin.sum(1, keepdims=True)).astype(np.float32)
+    sv = api.SoftMaxViterbi(A_lin, ml['ini_probs'], scaled=True)
+    sv.log_transition_matrix_T = ml['logA_T']                                # use the exact shipped log matrix
+    sv._decoder = Decoder(ml['logA_T'], ml['log_pi'])
+    for scaled in (0, 1):
+        probs = m[f'prob_ts_{scaled}'].copy()
+        if not np.array_equal(np.log(probs + tiny), m[f'log_prob_ts_{scaled}']):
+            continue
+        st = sv.viterbi_librosa_fn(probs)
+        assert np.array_equal(st < 320, m[f'voiced_{scaled}']) and np.array_equal(np.minimum(st, 319), m[f'bins_{scaled}'])
+        assert np.array_equal(probs, m[f'log_prob_ts_{scaled}'])
+
+    # Family D (imm): dense matrix, log-domain [S, T]
+    d = load('imm_dense.npz')
+    imm = api.ImmViterbi(20, 721)
+    if sha(imm.log_transition_matrix_T) == str(d['logA_T_sha']):
+        assert np.array_equal(imm.viterbi_librosa_fn(d['log_HF0']), d['states'])
+
+
+# ---- oracle on seeded inputs: shapes, ragged lengths, ties -----------------------------------------------------------
+
+SHAPES = [(1, 1, 1), (2, 3, 1), (7, 5, 3), (31, 40, 2), (32, 9, 33), (33, 17, 5), (96, 30, 4), (97, 50, 5), (128, 12, 3),
+          (192, 20, 6), (193, 25, 6), (200, 64, 9), (321, 100, 33), (361, 120, 70), (364, 30, 5), (365, 20, 3), (500, 15, 4)]
+
+
+@pytest.mark.parametrize('S,T,B', SHAPES)
+@pytest.mark.parametrize('kind', ['dyadic', 'tie_stress'])
+def test_against_oracle_shapes(Decoder, S, T, B, kind):
+    A, pi = synth.dyadic_hmm(S, seed=S, coarse=(kind == 'tie_stress'))
+    E = synth.batch(kind, B, T, S, seed0=10 + S)
+    want_p, want_s = c_oracle.decode_batch_c(A, pi, E)
+    for algo in algos_for(S):
+        p, s = Decoder(A, pi, algo=algo).decode_host(E)
+        assert np.array_equal(p, want_p), (algo, 'paths')
+        assert np.array_equal(s, want_s), (algo, 'scores')
+
+
+@pytest.mark.parametrize('state_set', ['dcnet', 'tonet'])
+@pytest.mark.parametrize('kind', ['dense_softmax', 'sparse_peaks'])
+def test_against_oracle_ragged_real_state_sets(Decoder, state_set, kind):
+    A, pi = hmm_params.synthetic_hmm(state_set)
+    logA_T, log_pi = hmm_params.log_params(A, pi)
+    S = len(pi)
+    B, T = 45, 150
+    E = synth.batch(kind, B, T, S, seed0=3)
+    rng = np.random.default_rng(S)
+    L = rng.integers(0, T + 1, size=B).astype(np.int32)
+    L[:6] = [T, 1, 0, 2, T, 3]
+    want_p, want_s = c_oracle.decode_batch_c(logA_T, log_pi, E, L)
+    for algo in ALGOS:
+        p, s = Decoder(logA_T, log_pi, algo=algo).decode_host(E, L)
+        assert np.array_equal(p, want_p) and np.array_equal(s, want_s), algo
+        assert (p[2] == -1).all() and s[2] == -np.inf and (p[1, 1:] == -1).all()
+
+
+def test_jdc_and_imm_state_sets_722(Decoder):
+    for name, add_tiny in (('jdc', True), ('imm', False)):
+        A, pi = hmm_params.synthetic_hmm(name)
+        logA_T, log_pi = hmm_params.log_params(A, pi, add_tiny=add_tiny)
+        E = synth.batch('dense_softmax', 5, 50, 722, seed0=5)
+        want_p, want_s = c_oracle.decode_batch_c(logA_T, log_pi, E)
+        p, s = Decoder(logA_T, log_pi).decode_host(E)
+        assert np.array_equal(p, want_p) and np.array_equal(s, want_s), name
+
+
+def test_T1_T2_tables_match_the_reference_tables(Decoder):
+    S, T, B = 61, 40, 3
+    A, pi = synth.dyadic_hmm(S, seed=2, coarse=True)
+    E = synth.batch('tie_stress', B, T, S, seed0=1)
+    dec = Decoder(A, pi)
+    dE = torch.as_tensor(E).cuda()
+    paths, scores, T1, T2 = dec.decode_device(dE, want_tables=True)
+    for b in range(B):
+        st, sc, rT1, rT2 = np_oracle.viterbi_log_np(A, pi, E[b], return_tables=True)
+        assert np.array_equal(T1[b].cpu().numpy(), rT1)
+        assert np.array_equal(T2[b].cpu().numpy().astype(np.int64)[1:], rT2[1:])
+        assert np.array_equal(paths[b].cpu().numpy(), st) and scores[b].item() == sc
+
+
+def test_minus_inf_entries_and_all_ties(Decoder):
+    S, T = 40, 25
+    A = np.full((S, S), -np.inf, np.float32)
+    A[np.arange(S), np.arange(S)] = 0
+    A[0, :] = 0
+    A[:, 3] = -1.5
+    pi = np.zeros(S, np.float32)
+    E = np.zeros((2, T, S), np.float32)
+    E[1] = synth.tie_stress((T, S), 4)
+    want_p, want_s = np_oracle.decode_batch_np(A, pi, E)
+    for algo in ALGOS:
+        p, s = Decoder(A, pi, algo=algo).decode_host(E)
+        assert np.array_equal(p, want_p) and np.array_equal(s, want_s), algo
+
+
+def test_device_api_lengths_and_untouched_inputs(Decoder):
+    S, T, B = 97, 33, 6
+    A, pi = synth.dyadic_hmm(S, seed=9)
+    E = synth.batch('dyadic', B, T, S, seed0=2)
+    L = np.asarray([33, 5, 0, 1, 20, 33], np.int32)
+    dE, dL = torch.as_tensor(E).cuda(), torch.as_tensor(L).cuda()
+    keep = dE.clone()
+    from viterbi_spl_b200 import decode_batch
+    p, s = decode_batch(dE, A, pi, dL)
+    assert p.is_cuda and p.dtype == torch.int64 and s.dtype == torch.float32
+    want_p, want_s = np_oracle.decode_batch_np(A, pi, E, L)
+    assert np.array_equal(p.cpu().numpy(), want_p) and np.array_equal(s.cpu().numpy(), want_s)
+    assert torch.equal(dE, keep)
+
+
+def test_c_abi_error_codes_on_device(cuda_lib):
+    S, T, B = 16, 4, 2
+    A, pi = synth.dyadic_hmm(S, seed=1)
+    dA, dpi = torch.as_tensor(A).cuda(), torch.as_tensor(pi).cuda()
+    dE = torch.zeros((B, T, S), device='cuda')
+    paths = torch.empty((B, T), dtype=torch.int64, device='cuda')
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device='cuda')
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert cuda_lib.vit_decode_f32(P(dA), P(dpi), P(dE), None, B, T, S, P(ws), 64, P(paths), None, None) == -3
+    assert cuda_lib.vit_decode_f32(P(dA), P(dpi), P(dE), None, B, T, S, ctypes.c_void_p(ws.data_ptr() + 8), 1 << 19,
+                                   P(paths), None, None) == -6
+    assert cuda_lib.vit_decode_f32(P(dA), P(dpi), P(dE), None, B, T, S, P(ws), ws.numel(), P(paths), None, None) == 0
+    torch.cuda.synchronize()
+    n0 = cuda_lib.vit_launch_count()
+    assert cuda_lib.vit_decode_f32(P(dA), P(dpi), P(dE), None, 0, T, S, P(ws), ws.numel(), P(paths), None, None) == 0
+    assert cuda_lib.vit_launch_count() == n0          # an empty batch launches nothing
+
+
+# ---- full size: BASELINE.json configuration, size-independent properties ------------------------------------------
+
+def test_full_size_properties(Decoder):
+    """1024 clips x 3000 frames x 361 states: (1) the two independent CUDA implementations agree bit-exactly;
+    (2) the returned score equals the fp32 score re-accumulated along the returned path with the reference's operation
+    order, T1[t][s_t] = fl(fl(T1[t-1][s_{t-1}] + B[s_t, s_{t-1}]) + E[t][s_t]); (3) a subset equals the CPU oracle;
+    (4) decoding is deterministic and invariant to the order of the clips in the batch."""
+    B, T, S = 1024, 3000, 361
+    A, pi = hmm_params.synthetic_hmm('tonet')
+    logA_T, log_pi = hmm_params.log_params(A, pi)
+    dev = torch.device('cuda')
+    E = synth.device_dense_softmax(B, T, S, seed=99, device=dev)
+    dec_c, dec_b = Decoder(logA_T, log_pi, algo='cluster'), Decoder(logA_T, log_pi, algo='backpointer')
+    p1, s1 = dec_c.decode_device(E)
+    p2, s2 = dec_b.decode_device(E)
+    assert torch.equal(p1, p2) and torch.equal(s1, s2)
+    del dec_b
+    # (2) score along the path, all clips at once, one fused pass per frame
+    dA, dpi = torch.as_tensor(logA_T, device=dev), torch.as_tensor(log_pi, device=dev)
+    ar = torch.arange(B, device=dev)
+    acc = dpi[p1[:, 0]] + E[ar, 0, p1[:, 0]]
+    for t in range(1, T):
+        acc = (acc + dA[p1[:, t], p1[:, t - 1]]) + E[ar, t, p1[:, t]]
+    assert torch.equal(acc, s1)
+    assert int(p1.min()) >= 0 and int(p1.max()) < S
+    # (3) oracle on a subset
+    sub = [0, 511, 1023]
+    want_p, want_s = c_oracle.decode_batch_c(logA_T, log_pi, E[sub].cpu().numpy())
+    assert np.array_equal(p1[sub].cpu().numpy(), want_p) and np.array_equal(s1[sub].cpu().numpy(), want_s)
+    # (4) determinism + permutation invariance on a slice (keeps memory bounded)
+    perm = torch.randperm(256, device=dev)
+    p3, s3 = dec_c.decode_device(E[:256][perm].contiguous())
+    assert torch.equal(p3, p1[:256][perm]) and torch.equal(s3, s1[:256][perm])

@@ -1,0 +1,138 @@
+"""CPU tests of the oracle itself (test infrastructure): the NumPy and C restatements of imm/tf_viterbi.py:75-109 must
+reproduce the golden vectors made by executing the reference's own functions, and the live reference when present."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, np_oracle, ref_loader
+from viterbi_spl_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def sha(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def exact_case(tag):
+    g = load('exact_inputs.npz')
+    S, T, coarse = (int(x) for x in g[tag + '_spec'])
+    A, pi = synth.dyadic_hmm(S, seed=S + T, coarse=bool(coarse))
+    E = synth.tie_stress((T, S), seed=7 * S + T) if coarse else synth.dyadic((T, S), seed=7 * S + T)
+    assert sha(A, pi, E) == str(g[tag + '_sha']), 'seeded exact inputs are not reproducible on this machine'
+    return A, pi, E, g[tag + '_states']
+
+
+EXACT_TAGS = ['dyadic361', 'ties361', 'dyadic722', 'ties97', 't1', 't2']
+
+
+@pytest.mark.parametrize('tag', EXACT_TAGS)
+@pytest.mark.parametrize('impl', ['np', 'c'])
+def test_exact_inputs_golden(tag, impl, oracle_c):
+    A, pi, E, want = exact_case(tag)
+    fn = np_oracle.viterbi_log_np if impl == 'np' else c_oracle.viterbi_log_c
+    states, score = fn(A, pi, E)
+    assert states.dtype == np.int64
+    assert np.array_equal(states, want)
+
+
+@pytest.mark.parametrize('impl', ['np', 'c'])
+def test_msnet_logdomain_golden(impl, oracle_c):
+    g = load('msnet_logdomain.npz')
+    fn = np_oracle.viterbi_log_np if impl == 'np' else c_oracle.viterbi_log_c
+    for kind in ('dense', 'sparse'):
+        states, _ = fn(g['logA_T'], g['log_pi'], g['E_' + kind])
+        assert np.array_equal(states, g['states_' + kind]), kind
+
+
+def test_family_goldens_logdomain(oracle_c):
+    g = load('family_a.npz')
+    assert np.array_equal(c_oracle.viterbi_log_c(g['logA_T'], g['log_pi'], g['log_probs_ts'])[0], g['states'])
+    g = load('tonet_family_b.npz')
+    E = np.require(g['log_probs_st'].T, requirements=['C'])
+    assert np.array_equal(np_oracle.viterbi_log_np(g['logA_T'], g['log_pi'], E)[0], g['states'])
+    g = load('msnet_softmax_viterbi.npz')
+    m = load('msnet_logdomain.npz')
+    for scaled in (0, 1):
+        st = c_oracle.viterbi_log_c(m['logA_T'], m['log_pi'], g[f'log_prob_ts_{scaled}'])[0]
+        assert np.array_equal(st < 320, g[f'voiced_{scaled}'])
+        assert np.array_equal(np.minimum(st, 319), g[f'bins_{scaled}'])
+
+
+def test_family_a_np_matches_golden_when_libm_matches():
+    g = load('family_a.npz')
+    tiny = np.finfo(np.float32).tiny
+    if not np.array_equal(np.log(g['probs_st'].T + tiny), g['log_probs_ts']):
+        pytest.skip('this machine\'s float32 log differs from the one that made the golden (expected: not correctly rounded)')
+    st = np_oracle.family_a_np(transition_matrix=g['A'], prob_init=g['pi'], probs_st=g['probs_st'])
+    assert np.array_equal(st, g['states'])
+
+
+def test_c_equals_np_with_tables(oracle_c):
+    rng = np.random.default_rng(3)
+    for S, T in [(1, 1), (2, 7), (33, 50), (130, 40)]:
+        A, pi = synth.dyadic_hmm(S, seed=S, coarse=(S % 2 == 0))
+        E = synth.tie_stress((T, S), seed=T) if S % 2 else synth.dyadic((T, S), seed=T)
+        s1, sc1, T1a, T2a = np_oracle.viterbi_log_np(A, pi, E, return_tables=True)
+        s2, sc2, T1b, T2b = c_oracle.viterbi_log_c(A, pi, E, return_tables=True)
+        assert np.array_equal(s1, s2) and sc1 == sc2
+        assert np.array_equal(T1a, T1b)
+        assert np.array_equal(T2a[1:], T2b[1:])
+
+
+def test_batch_ragged_and_threads(oracle_c):
+    S, T, B = 47, 30, 11
+    A, pi = synth.dyadic_hmm(S, seed=1)
+    E = synth.batch('dyadic', B, T, S, seed0=5)
+    L = np.asarray([30, 0, 1, 2, 17, 30, 29, 3, 0, 8, 30], np.int32)
+    p1, s1 = np_oracle.decode_batch_np(A, pi, E, L)
+    for nt in (1, 3, 0):
+        p2, s2 = c_oracle.decode_batch_c(A, pi, E, L, nthreads=nt)
+        assert np.array_equal(p1, p2) and np.array_equal(s1, s2)
+    assert (p1[1] == -1).all() and s1[1] == -np.inf and (p1[2, 1:] == -1).all()
+
+
+def test_minus_inf_and_all_equal_rows(oracle_c):
+    S, T = 9, 6
+    A = np.full((S, S), -np.inf, np.float32)
+    A[np.arange(S), np.arange(S)] = 0
+    A[0, :] = 0
+    pi = np.zeros(S, np.float32)
+    E = np.zeros((T, S), np.float32)
+    s1, _ = np_oracle.viterbi_log_np(A, pi, E)
+    s2, _ = c_oracle.viterbi_log_c(A, pi, E)
+    assert np.array_equal(s1, s2) and (s1 == 0).all()       # every cell tied: first maximum wins everywhere
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='/root/reference not present (GPU box)')
+def test_live_reference_agrees():
+    ref = ref_loader.log_domain_decode()
+    for seed, (S, T) in enumerate([(61, 90), (321, 40)]):
+        A, pi = synth.dyadic_hmm(S, seed=seed, coarse=bool(seed % 2))
+        E = synth.dense_softmax(T, S, seed=seed)
+        want = ref(log_transition_matrix_T=A, log_prob_init=pi, log_probs_st=np.require(E.T, requirements=['C']))
+        assert np.array_equal(np_oracle.viterbi_log_np(A, pi, E)[0], want)
+        assert np.array_equal(c_oracle.viterbi_log_c(A, pi, E)[0], want)
+        assert np.array_equal(np_oracle.viterbi_log_st_np(log_transition_matrix_T=A, log_prob_init=pi,
+                                                          log_probs_st=np.require(E.T, requirements=['C'])), want)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='/root/reference not present (GPU box)')
+def test_live_reference_family_a_and_numba():
+    g = load('family_a.npz')
+    fa = ref_loader.family_a_decode()
+    want = fa(transition_matrix=g['A'], prob_init=g['pi'], probs_st=np.asfortranarray(g['probs_st']))
+    assert np.array_equal(np_oracle.family_a_np(transition_matrix=g['A'], prob_init=g['pi'], probs_st=g['probs_st']), want)
+    nb = ref_loader.numba_core()
+    got = nb(np.require(g['A'].T, requirements=['C']).copy(), g['pi'].copy(),
+             np.require(g['probs_st'].T, requirements=['C']).copy())
+    assert np.array_equal(got, want)

@@ -33,9 +33,10 @@ class ViterbiDecoder:
             raise RuntimeError('viterbi_spl_b200 needs a CUDA device (B200); there is no CPU fallback')
         self.lib = _lib.load()
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
-        A = torch.as_tensor(np.asarray(log_transition_matrix_T) if not torch.is_tensor(log_transition_matrix_T)
-                            else log_transition_matrix_T)
-        pi = torch.as_tensor(np.asarray(log_prob_init) if not torch.is_tensor(log_prob_init) else log_prob_init)
+        # (copies: the reference marks its parameter arrays read-only, which torch cannot wrap)
+        A = log_transition_matrix_T if torch.is_tensor(log_transition_matrix_T) else \
+            torch.from_numpy(np.array(log_transition_matrix_T, copy=True))
+        pi = log_prob_init if torch.is_tensor(log_prob_init) else torch.from_numpy(np.array(log_prob_init, copy=True))
         assert A.dtype == torch.float32 and pi.dtype == torch.float32, 'log-domain parameters must be float32'
         assert A.ndim == 2 and A.shape[0] == A.shape[1], 'log_transition_matrix_T must be [S, S]'
         self.S = int(A.shape[0])
