@@ -315,7 +315,10 @@ def run_ours(a):
             traffic = json.load(fh).get('dram_bytes_per_launch')
     except Exception:
         pass
-    roofline = {'bound': 'fp32_alu', 'kernel': 'cluster_forward_kernel', 'achieved': cells_per_s / 1e12,
+    algo_res = dec.algo if dec.algo else _lib.load().vit_select_algo(B, T, S)
+    algo_name = {1: 'backpointer', 2: 'cluster', 3: 'tmem'}.get(algo_res, str(algo_res))
+    kernel_name = {1: 'bp_forward_kernel', 2: 'cluster_forward_kernel', 3: 'tmem_forward_kernel'}.get(algo_res, '?')
+    roofline = {'bound': 'fp32_alu', 'kernel': kernel_name, 'achieved': cells_per_s / 1e12,
                 'peak': alu_peak / 1e12, 'unit': 'Tcell/s', 'frac': cells_per_s / alu_peak,
                 'peak_definition': f'148 SMs x 64 cells/clk (FADD+FMNMX, 2 issue slots per cell) x {sm_mhz_peak:.0f} MHz '
                                    f'({peak_src} sm_max_mhz)',
@@ -329,7 +332,7 @@ def run_ours(a):
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name(a), 'clips_per_gpu': B, 'frames': T, 'states': S,
-                   'algo': {0: 'auto', 1: 'backpointer', 2: 'cluster'}.get(dec.algo, str(dec.algo)),
+                   'algo': algo_name,
                    'l2': 'inputs (4.4 GB emissions per step) are far larger than the 126 MB L2',
                    'parallelism': f'{world} x independent clip shards, no data-path collective'},
         'roofline': roofline, 'roofline_hbm': roofline_hbm,

@@ -50,7 +50,11 @@ typedef enum vit_algo {
   /* persistent thread-block-cluster kernel: logA^T column-sharded and resident in shared memory, delta exchanged
    * through distributed shared memory, register-tiled FADD2/FMNMX3 max-plus, delta history (fp32) in the workspace
    * and the argmax resolved lazily by the backtrace only along the decoded path (bit-identical result). */
-  VIT_ALGO_CLUSTER = 2
+  VIT_ALGO_CLUSTER = 2,
+  /* the throughput path: as VIT_ALGO_CLUSTER, but the resident logA^T shard lives in TENSOR MEMORY (tcgen05.ld into
+   * registers) so that 2-CTA clusters -- which pack all 148 SMs, 4-CTA clusters strand 16 -- can hold a 361-state
+   * shard; 7 clips x 6 targets per thread, two pipelines per CTA.  S <= 384.  Supports frame ranges. */
+  VIT_ALGO_TMEM = 3
 } vit_algo;
 
 /* Optional extras for vit_decode_f32_ex (all may be zero/NULL). */
@@ -62,6 +66,14 @@ typedef struct vit_decode_opts {
   float* d_delta;            /* [B][T_max][S] out: the reference's T1 table (imm/tf_viterbi.py:91,94,100). */
   void* ev_forward_begin;    /* optional cudaEvent_t recorded on `stream` right before the forward (recursion) kernel */
   void* ev_forward_end;      /* optional cudaEvent_t recorded right after it (bench.py times the kernel with these) */
+  /* Frame range (VIT_ALGO_TMEM only): run the recursion over frames [frame_begin, frame_end) only; frame_end = 0
+   * means T_max.  A range with frame_begin > 0 resumes from the delta history that an earlier call on the SAME
+   * workspace left behind, so a host can upload a long batch in time slabs and overlap each copy with the recursion
+   * over the previous slab.  skip_backtrace != 0 leaves d_paths / d_scores untouched (all but the last slab). */
+  int32_t frame_begin;
+  int32_t frame_end;
+  int32_t skip_backtrace;
+  int32_t reserved2;
 } vit_decode_opts;
 
 /* Library version (VIT_B200_VERSION of the built library). */
@@ -107,6 +119,15 @@ int vit_decode_f32_ex(const float* d_logA_T, const float* d_log_pi, const float*
                       const int32_t* d_lengths, int B, int T_max, int S,
                       void* d_workspace, size_t workspace_bytes,
                       int64_t* d_paths, float* d_scores, const vit_decode_opts* opts, void* stream);
+
+/*
+ * Host -> device upload of frames [frame_begin, frame_end) of every clip of a [B][T_max][S] float32 batch: one strided
+ * 2-D async copy on `stream` (h_log_emis should be page-locked for the copy to be asynchronous).  Together with the
+ * frame ranges of vit_decode_f32_ex this lets a host overlap the PCIe transfer of time slab k+1 with the recursion
+ * over slab k.  (The reference hands the decoder one host array per recording: dcnet/softmax_viterbi.py:3033-3040.)
+ */
+int vit_upload_frames_f32(float* d_log_emis, const float* h_log_emis, int B, int T_max, int S,
+                          int frame_begin, int frame_end, void* stream);
 
 #ifdef __cplusplus
 }

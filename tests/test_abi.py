@@ -49,10 +49,14 @@ def test_version_and_strerror(cuda_lib):
 
 def test_workspace_and_algo_selection(cuda_lib):
     from viterbi_spl_b200 import _lib
-    # S = 361 / 321 fit the cluster kernel; S = 722 falls back to the backpointer kernel
-    assert cuda_lib.vit_select_algo(1024, 3000, 361) == _lib.ALGO_CLUSTER
-    assert cuda_lib.vit_select_algo(1, 3000, 321) == _lib.ALGO_CLUSTER
-    assert cuda_lib.vit_select_algo(16, 100, 722) == _lib.ALGO_BACKPOINTER
+    # every pitch-bin state set (321 / 361 / 722) fits the tensor-memory kernel; beyond 8 x 192 states the generic
+    # backpointer kernel takes over
+    assert cuda_lib.vit_select_algo(1024, 3000, 361) == _lib.ALGO_TMEM
+    assert cuda_lib.vit_select_algo(1, 3000, 321) == _lib.ALGO_TMEM
+    assert cuda_lib.vit_select_algo(16, 100, 722) == _lib.ALGO_TMEM
+    assert cuda_lib.vit_select_algo(16, 100, 1537) == _lib.ALGO_BACKPOINTER
+    n = _lib.workspace_bytes(1024, 3000, 361, _lib.ALGO_TMEM)
+    assert 1024 * 3000 * 361 * 4 <= n <= 1024 * 3000 * 361 * 4 + (1 << 20)       # fp32 delta history + packed logA^T
     n = _lib.workspace_bytes(1024, 3000, 361, _lib.ALGO_CLUSTER)
     assert 1024 * 3000 * 361 * 4 <= n <= 1024 * 3000 * 361 * 4 + (1 << 20)       # fp32 delta history + packed logA^T
     n = _lib.workspace_bytes(1024, 3000, 361, _lib.ALGO_BACKPOINTER)

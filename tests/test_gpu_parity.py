@@ -20,7 +20,7 @@ from viterbi_spl_b200 import hmm_params, synth
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
-ALGOS = ['cluster', 'backpointer']
+ALGOS = ['tmem', 'cluster', 'backpointer']
 
 
 def load(name):
@@ -42,7 +42,11 @@ def Decoder(cuda_lib):
 
 
 def algos_for(S):
-    return ALGOS if S <= 364 else ['backpointer', 'auto']
+    from viterbi_spl_b200 import _lib
+    if S <= 364:
+        return ALGOS
+    tmem_ok = _lib.load().vit_select_algo(1, 1, S) == _lib.ALGO_TMEM
+    return ['tmem', 'backpointer', 'auto'] if tmem_ok else ['backpointer', 'auto']
 
 
 # ---- golden vectors (made by the reference's own code) ------------------------------------------------------------
@@ -152,8 +156,9 @@ def test_reference_entry_points(Decoder):
 
 # ---- oracle on seeded inputs: shapes, ragged lengths, ties -----------------------------------------------------------
 
-SHAPES = [(1, 1, 1), (2, 3, 1), (7, 5, 3), (31, 40, 2), (32, 9, 33), (33, 17, 5), (96, 30, 4), (97, 50, 5), (128, 12, 3),
-          (192, 20, 6), (193, 25, 6), (200, 64, 9), (321, 100, 33), (361, 120, 70), (364, 30, 5), (365, 20, 3), (500, 15, 4)]
+SHAPES = [(1, 1, 1), (2, 3, 1), (7, 5, 3), (31, 40, 2), (32, 9, 33), (33, 17, 5), (64, 21, 15), (96, 30, 4), (97, 50, 5),
+          (128, 12, 3), (160, 14, 8), (192, 20, 6), (193, 25, 6), (200, 64, 9), (321, 100, 33), (361, 120, 70), (364, 30, 5),
+          (365, 20, 3), (384, 18, 16), (385, 16, 9), (500, 15, 4), (722, 24, 17), (769, 9, 15)]
 
 
 @pytest.mark.parametrize('S,T,B', SHAPES)
@@ -192,8 +197,9 @@ def test_jdc_and_imm_state_sets_722(Decoder):
         logA_T, log_pi = hmm_params.log_params(A, pi, add_tiny=add_tiny)
         E = synth.batch('dense_softmax', 5, 50, 722, seed0=5)
         want_p, want_s = c_oracle.decode_batch_c(logA_T, log_pi, E)
-        p, s = Decoder(logA_T, log_pi).decode_host(E)
-        assert np.array_equal(p, want_p) and np.array_equal(s, want_s), name
+        for algo in ('auto', 'tmem', 'backpointer'):
+            p, s = Decoder(logA_T, log_pi, algo=algo).decode_host(E)
+            assert np.array_equal(p, want_p) and np.array_equal(s, want_s), (name, algo)
 
 
 def test_T1_T2_tables_match_the_reference_tables(Decoder):
@@ -223,6 +229,27 @@ def test_minus_inf_entries_and_all_ties(Decoder):
     for algo in ALGOS:
         p, s = Decoder(A, pi, algo=algo).decode_host(E)
         assert np.array_equal(p, want_p) and np.array_equal(s, want_s), algo
+
+
+@pytest.mark.parametrize('S,T,B,slab', [(361, 64, 40, 16), (361, 50, 9, 7), (97, 33, 6, 1), (321, 40, 15, 39), (722, 30, 16, 11)])
+def test_frame_slabs_resume_from_the_delta_history(Decoder, S, T, B, slab):
+    """The recursion run as consecutive frame ranges [t0, t1) (what decode_host does to overlap the upload of the next
+    time slab with the decode of the current one) is bit-identical to one pass -- ragged lengths included."""
+    A, pi = synth.dyadic_hmm(S, seed=S + 1, coarse=True)
+    E = synth.batch('tie_stress', B, T, S, seed0=77)
+    L = np.random.default_rng(S + T).integers(0, T + 1, size=B).astype(np.int32)
+    L[0] = T
+    want_p, want_s = c_oracle.decode_batch_c(A, pi, E, L)
+    dec = Decoder(A, pi, algo='tmem')
+    p, s = dec.decode_host(E, L, slab_frames=slab)
+    assert np.array_equal(p, want_p) and np.array_equal(s, want_s)
+    dE, dL = torch.as_tensor(E).cuda(), torch.as_tensor(L).cuda()
+    paths = scores = None
+    for t0 in range(0, T, slab):
+        last = t0 + slab >= T
+        out = dec.decode_device(dE, dL, paths, scores, frame_range=(t0, min(T, t0 + slab)), backtrace=last)
+        paths, scores = out
+    assert np.array_equal(paths.cpu().numpy(), want_p) and np.array_equal(scores.cpu().numpy(), want_s)
 
 
 def test_device_api_lengths_and_untouched_inputs(Decoder):
@@ -261,7 +288,7 @@ def test_c_abi_error_codes_on_device(cuda_lib):
 # ---- full size: BASELINE.json configuration, size-independent properties ------------------------------------------
 
 def test_full_size_properties(Decoder):
-    """1024 clips x 3000 frames x 361 states: (1) the two independent CUDA implementations agree bit-exactly;
+    """1024 clips x 3000 frames x 361 states: (1) the three independent CUDA implementations agree bit-exactly;
     (2) the returned score equals the fp32 score re-accumulated along the returned path with the reference's operation
     order, T1[t][s_t] = fl(fl(T1[t-1][s_{t-1}] + B[s_t, s_{t-1}]) + E[t][s_t]); (3) a subset equals the CPU oracle;
     (4) decoding is deterministic and invariant to the order of the clips in the batch."""
@@ -270,11 +297,16 @@ def test_full_size_properties(Decoder):
     logA_T, log_pi = hmm_params.log_params(A, pi)
     dev = torch.device('cuda')
     E = synth.device_dense_softmax(B, T, S, seed=99, device=dev)
-    dec_c, dec_b = Decoder(logA_T, log_pi, algo='cluster'), Decoder(logA_T, log_pi, algo='backpointer')
+    dec_c, dec_b = Decoder(logA_T, log_pi, algo='tmem'), Decoder(logA_T, log_pi, algo='backpointer')
     p1, s1 = dec_c.decode_device(E)
     p2, s2 = dec_b.decode_device(E)
     assert torch.equal(p1, p2) and torch.equal(s1, s2)
-    del dec_b
+    del dec_b, p2, s2
+    dec_k = Decoder(logA_T, log_pi, algo='cluster')
+    p2, s2 = dec_k.decode_device(E)
+    assert torch.equal(p1, p2) and torch.equal(s1, s2)
+    del dec_k, p2, s2
+    torch.cuda.empty_cache()
     # (2) score along the path, all clips at once, one fused pass per frame
     dA, dpi = torch.as_tensor(logA_T, device=dev), torch.as_tensor(log_pi, device=dev)
     ar = torch.arange(B, device=dev)

@@ -5,7 +5,7 @@ import numpy as np, torch
 from viterbi_spl_b200 import ViterbiDecoder, hmm_params, synth
 from oracle import c_oracle
 
-def check(name, logA_T, log_pi, E, lengths=None, algos=('backpointer', 'cluster')):
+def check(name, logA_T, log_pi, E, lengths=None, algos=('backpointer', 'cluster', 'tmem')):
     ref_p, ref_s = c_oracle.decode_batch_c(logA_T, log_pi, E, lengths)
     for algo in algos:
         try:
@@ -35,4 +35,4 @@ E = synth.batch('sparse_peaks', 36, 150, 361, seed0=4)
 check('tonet sparse', logA_T, log_pi, E)
 A, pi = hmm_params.synthetic_hmm('imm'); logA_T, log_pi = hmm_params.log_params(A, pi, add_tiny=False)
 E = synth.batch('dense_softmax', 4, 60, 722, seed0=5)
-check('imm dense S=722', logA_T, log_pi, E, algos=('backpointer', 'auto'))
+check('imm dense S=722', logA_T, log_pi, E, algos=('backpointer', 'tmem'))

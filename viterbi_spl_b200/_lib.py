@@ -9,19 +9,21 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libvit_b200.so')
 
 VIT_OK = 0
-ALGO_AUTO, ALGO_BACKPOINTER, ALGO_CLUSTER = 0, 1, 2
-ALGO_NAMES = {'auto': ALGO_AUTO, 'backpointer': ALGO_BACKPOINTER, 'cluster': ALGO_CLUSTER}
+ALGO_AUTO, ALGO_BACKPOINTER, ALGO_CLUSTER, ALGO_TMEM = 0, 1, 2, 3
+ALGO_NAMES = {'auto': ALGO_AUTO, 'backpointer': ALGO_BACKPOINTER, 'cluster': ALGO_CLUSTER, 'tmem': ALGO_TMEM}
 
 # every symbol include/vit_b200.h declares (tests/test_abi.py checks the built library exports them all)
 EXPORTS = ['vit_version', 'vit_strerror', 'vit_last_cuda_error', 'vit_launch_count', 'vit_select_algo',
-           'vit_workspace_bytes', 'vit_decode_f32', 'vit_decode_f32_ex']
+           'vit_workspace_bytes', 'vit_decode_f32', 'vit_decode_f32_ex', 'vit_upload_frames_f32']
 
 
 class DecodeOpts(ctypes.Structure):
     """struct vit_decode_opts"""
     _fields_ = [('algo', ctypes.c_int32), ('reserved', ctypes.c_int32),
                 ('d_backpointers', ctypes.c_void_p), ('d_delta', ctypes.c_void_p),
-                ('ev_forward_begin', ctypes.c_void_p), ('ev_forward_end', ctypes.c_void_p)]
+                ('ev_forward_begin', ctypes.c_void_p), ('ev_forward_end', ctypes.c_void_p),
+                ('frame_begin', ctypes.c_int32), ('frame_end', ctypes.c_int32),
+                ('skip_backtrace', ctypes.c_int32), ('reserved2', ctypes.c_int32)]
 
 
 class VitError(RuntimeError):
@@ -56,6 +58,8 @@ def load():
     L.vit_decode_f32.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp, vp, vp]
     L.vit_decode_f32_ex.restype = ci
     L.vit_decode_f32_ex.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp, vp, ctypes.POINTER(DecodeOpts), vp]
+    L.vit_upload_frames_f32.restype = ci
+    L.vit_upload_frames_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
     _lib = L
     return L
 

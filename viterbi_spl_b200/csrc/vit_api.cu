@@ -30,6 +30,14 @@ int cluster_decode(const float* logA_T, const float* log_pi, const float* log_em
                    int T_max, int S, void* workspace, size_t workspace_bytes, int64_t* paths, float* scores,
                    float* delta_out, cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t stream);
 
+// vit_tmem.cu
+size_t tmem_workspace_bytes(int B, int T_max, int S);
+bool tmem_supported(int S);
+int tmem_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
+                int T_max, int S, void* workspace, size_t workspace_bytes, int64_t* paths, float* scores,
+                float* delta_out, int t_begin, int t_end, bool do_backtrace, cudaEvent_t ev0, cudaEvent_t ev1,
+                cudaStream_t stream);
+
 static int check_shape(int B, int T_max, int S) {
   if (B < 0 || T_max < 1 || S < 1) return VIT_ERR_INVALID_ARGUMENT;
   if (S > 65535) return VIT_ERR_STATES_TOO_MANY;
@@ -38,9 +46,11 @@ static int check_shape(int B, int T_max, int S) {
 
 static int resolve_algo(int algo, int S, bool want_bp) {
   if (want_bp) return VIT_ALGO_BACKPOINTER;
-  if (algo == VIT_ALGO_AUTO) return cluster_supported(S) ? VIT_ALGO_CLUSTER : VIT_ALGO_BACKPOINTER;
+  if (algo == VIT_ALGO_AUTO)
+    return tmem_supported(S) ? VIT_ALGO_TMEM : (cluster_supported(S) ? VIT_ALGO_CLUSTER : VIT_ALGO_BACKPOINTER);
   if (algo == VIT_ALGO_BACKPOINTER) return algo;
   if (algo == VIT_ALGO_CLUSTER) return cluster_supported(S) ? algo : VIT_ERR_UNSUPPORTED_ALGO;
+  if (algo == VIT_ALGO_TMEM) return tmem_supported(S) ? algo : VIT_ERR_UNSUPPORTED_ALGO;
   return VIT_ERR_INVALID_ARGUMENT;
 }
 
@@ -81,7 +91,9 @@ int vit_workspace_bytes(int B, int T_max, int S, int algo, size_t* out_bytes) {
   if (rc != VIT_OK) return rc;
   int a = resolve_algo(algo, S, false);
   if (a < 0) return a;
-  *out_bytes = (a == VIT_ALGO_CLUSTER) ? cluster_workspace_bytes(B, T_max, S) : bp_workspace_bytes(B, T_max, S, false);
+  *out_bytes = (a == VIT_ALGO_TMEM)      ? tmem_workspace_bytes(B, T_max, S)
+               : (a == VIT_ALGO_CLUSTER) ? cluster_workspace_bytes(B, T_max, S)
+                                         : bp_workspace_bytes(B, T_max, S, false);
   return VIT_OK;
 }
 
@@ -102,6 +114,15 @@ int vit_decode_f32_ex(const float* d_logA_T, const float* d_log_pi, const float*
   cudaStream_t st = (cudaStream_t)stream;
   cudaEvent_t ev0 = opts ? (cudaEvent_t)opts->ev_forward_begin : nullptr;
   cudaEvent_t ev1 = opts ? (cudaEvent_t)opts->ev_forward_end : nullptr;
+  const int f_begin = opts ? opts->frame_begin : 0;
+  const int f_end = (opts && opts->frame_end > 0) ? opts->frame_end : T_max;
+  const bool skip_bt = opts && opts->skip_backtrace != 0;
+  if (algo == VIT_ALGO_TMEM) {
+    // bit 3 of the S check: the shared lazy-argmax backtrace handles S <= 384, which is also the TMEM plan's limit
+    return tmem_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_paths,
+                       d_scores, delta_out, f_begin, f_end, !skip_bt, ev0, ev1, st);
+  }
+  if (f_begin != 0 || f_end != T_max || skip_bt) return VIT_ERR_UNSUPPORTED_ALGO;   // frame ranges: VIT_ALGO_TMEM only
   if (algo == VIT_ALGO_CLUSTER)
     return cluster_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes,
                           d_paths, d_scores, delta_out, ev0, ev1, st);
@@ -114,6 +135,21 @@ int vit_decode_f32(const float* d_logA_T, const float* d_log_pi, const float* d_
                    float* d_scores, void* stream) {
   return vit_decode_f32_ex(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes,
                            d_paths, d_scores, nullptr, stream);
+}
+
+int vit_upload_frames_f32(float* d_log_emis, const float* h_log_emis, int B, int T_max, int S, int frame_begin,
+                          int frame_end, void* stream) {
+  int rc = check_shape(B, T_max, S);
+  if (rc != VIT_OK) return rc;
+  if (!d_log_emis || !h_log_emis || frame_begin < 0 || frame_end > T_max || frame_begin > frame_end)
+    return VIT_ERR_INVALID_ARGUMENT;
+  if (B == 0 || frame_begin == frame_end) return VIT_OK;
+  const size_t pitch = (size_t)T_max * S * sizeof(float);
+  const size_t width = (size_t)(frame_end - frame_begin) * S * sizeof(float);
+  const size_t off = (size_t)frame_begin * S;
+  VIT_CUDA_TRY(cudaMemcpy2DAsync(d_log_emis + off, pitch, h_log_emis + off, pitch, width, (size_t)B,
+                                 cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return VIT_OK;
 }
 
 }  // extern "C"

@@ -274,8 +274,8 @@ cluster_forward_kernel(const float* __restrict__ packedA, const float* __restric
 // Lazy-argmax backtrace: one warp per clip.  s_{T-1} = argmax_j delta_{T-1}[j]; then for t = T-1 .. 1
 //   s_{t-1} = argmax_i fl32(delta_{t-1}[i] + logA^T[s_t][i])   -- the entry T2[t][s_t] of the reference's table,
 // recomputed with the same fp32 add and the same first-maximum rule (imm/tf_viterbi.py:98-99, 103-107).
-constexpr int kBtMaxPerLane = 12;   // S <= 384
-
+// kBtMaxPerLane: source states per lane held in registers (12 -> S <= 384, 24 -> S <= 768, 48 -> S <= 1536)
+template <int kBtMaxPerLane>
 __global__ void __launch_bounds__(128)
 cluster_backtrace_kernel(const float* __restrict__ logA_T, const float* __restrict__ hist,
                          const int32_t* __restrict__ lengths, int B, int T_max, int S,
@@ -358,6 +358,24 @@ cluster_backtrace_kernel(const float* __restrict__ logA_T, const float* __restri
   }
 }
 
+// shared with vit_tmem.cu: both forward kernels leave the same fp32 delta history behind
+int launch_hist_backtrace(const float* logA_T, const float* hist, const int32_t* lengths, int B, int T_max, int S,
+                          int64_t* paths, float* scores, cudaStream_t stream) {
+  const int warps_per_block = 4;
+  const dim3 grid((B + warps_per_block - 1) / warps_per_block), block(warps_per_block * 32);
+  if (S <= 32 * 12)
+    cluster_backtrace_kernel<12><<<grid, block, 0, stream>>>(logA_T, hist, lengths, B, T_max, S, paths, scores);
+  else if (S <= 32 * 24)
+    cluster_backtrace_kernel<24><<<grid, block, 0, stream>>>(logA_T, hist, lengths, B, T_max, S, paths, scores);
+  else if (S <= 32 * 48)
+    cluster_backtrace_kernel<48><<<grid, block, 0, stream>>>(logA_T, hist, lengths, B, T_max, S, paths, scores);
+  else
+    return VIT_ERR_UNSUPPORTED_ALGO;
+  note_launch();
+  VIT_CUDA_TRY(cudaGetLastError());
+  return VIT_OK;
+}
+
 size_t cluster_workspace_bytes(int B, int T_max, int S) {
   ClusterPlan p;
   if (!make_plan(S, &p)) return 0;
@@ -426,12 +444,7 @@ int cluster_decode(const float* logA_T, const float* log_pi, const float* log_em
   note_launch();
   if (ev1) VIT_CUDA_TRY(cudaEventRecord(ev1, stream));
 
-  const int warps_per_block = 4;
-  cluster_backtrace_kernel<<<(B + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
-      logA_T, hist, lengths, B, T_max, S, paths, scores);
-  note_launch();
-  VIT_CUDA_TRY(cudaGetLastError());
-  return VIT_OK;
+  return launch_hist_backtrace(logA_T, hist, lengths, B, T_max, S, paths, scores, stream);
 }
 
 }  // namespace vit

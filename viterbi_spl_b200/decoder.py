@@ -47,6 +47,8 @@ class ViterbiDecoder:
         self.algo = _lib.ALGO_NAMES[algo] if isinstance(algo, str) else int(algo)
         self._ws = None
         self._pinned = {}
+        self._dev_emis = None
+        self._copy_stream = None
 
     # ---- device path ---------------------------------------------------------------------------------------
     def _workspace(self, nbytes):
@@ -56,11 +58,14 @@ class ViterbiDecoder:
         return self._ws
 
     def decode_device(self, log_emis, lengths=None, paths=None, scores=None, want_tables=False, stream=None,
-                      forward_events=None):
+                      forward_events=None, frame_range=None, backtrace=True):
         """log_emis: CUDA float32 [B, T, S] contiguous; lengths: CUDA int32 [B] or None.
         Returns (paths int64 [B, T], scores float32 [B]) CUDA tensors (+ (T1 float32, T2 uint16) if want_tables).
         Asynchronous on `stream` (default: torch's current stream).  forward_events: optional pair of
-        torch.cuda.Event(enable_timing=True) recorded by the library around the forward kernel."""
+        torch.cuda.Event(enable_timing=True) recorded by the library around the forward kernel.
+        frame_range=(t0, t1) runs the recursion over those frames only, resuming (t0 > 0) from the delta history the
+        previous call left in this decoder's workspace; backtrace=False skips the backtrace (all but the last range).
+        Frame ranges need the tmem algorithm."""
         assert log_emis.is_cuda and log_emis.dtype == torch.float32 and log_emis.is_contiguous()
         B, T, S = log_emis.shape
         assert S == self.S, f'emissions have {S} states, model has {self.S}'
@@ -88,6 +93,10 @@ class ViterbiDecoder:
                             ev.record(st)
                     opts.ev_forward_begin = forward_events[0].cuda_event
                     opts.ev_forward_end = forward_events[1].cuda_event
+                if frame_range is not None:
+                    opts.frame_begin, opts.frame_end = int(frame_range[0]), int(frame_range[1])
+                    assert 0 <= opts.frame_begin < opts.frame_end <= T, 'frame_range must be a non-empty range in [0, T]'
+                opts.skip_backtrace = 0 if backtrace else 1
                 rc = self.lib.vit_decode_f32_ex(_ptr(self.logA_T), _ptr(self.log_pi), _ptr(log_emis), _ptr(lengths),
                                                 B, T, S, _ptr(ws), ws.numel(), _ptr(paths), _ptr(scores),
                                                 ctypes.byref(opts), ctypes.c_void_p(st.cuda_stream))
@@ -105,9 +114,20 @@ class ViterbiDecoder:
             self._pinned[key] = buf
         return buf[:n].view(*shape)
 
-    def decode_host(self, log_emis, lengths=None):
+    def supports_frame_slabs(self):
+        """True if this decoder's algorithm can run the recursion as consecutive frame ranges (tmem)."""
+        algo = self.algo
+        if algo == _lib.ALGO_AUTO:
+            algo = self.lib.vit_select_algo(1, 1, self.S)
+        return algo == _lib.ALGO_TMEM
+
+    def decode_host(self, log_emis, lengths=None, slab_frames=None):
         """log_emis: host float32 array [B, T, S] (NumPy or CPU tensor).  Copies host->device, decodes, copies the
-        paths and scores back; returns NumPy (paths int64 [B, T], scores float32 [B])."""
+        paths and scores back; returns NumPy (paths int64 [B, T], scores float32 [B]).
+
+        Large batches are uploaded in time slabs of `slab_frames` frames (default: about T/8 once the batch exceeds
+        64 MB) on a copy stream while the recursion over the previous slab runs on the compute stream, so the
+        end-to-end time is max(PCIe copy, decode) instead of their sum."""
         E = torch.as_tensor(log_emis)
         assert E.dtype == torch.float32 and E.ndim == 3
         B, T, S = E.shape
@@ -117,17 +137,47 @@ class ViterbiDecoder:
             else:
                 src = self._pinned_buf('emis', (B, T, S), torch.float32)
                 src.copy_(E)
-            dE = src.to(self.device, non_blocking=True)
             dL = None
             if lengths is not None:
                 dL = torch.as_tensor(np.asarray(lengths, np.int32)).to(self.device)
-            paths, scores = self.decode_device(dE, dL)
+            if slab_frames is None:
+                slab_frames = T if B * T * S * 4 < (64 << 20) else max(64, -(-T // 8))
+            if slab_frames >= T or B == 0 or not self.supports_frame_slabs():
+                dE = src.to(self.device, non_blocking=True)
+                paths, scores = self.decode_device(dE, dL)
+            else:
+                paths, scores = self._decode_host_slabs(src, dL, int(slab_frames))
             hp = self._pinned_buf('paths', (B, T), torch.int64)
             hs = self._pinned_buf('scores', (B,), torch.float32)
             hp.copy_(paths, non_blocking=True)
             hs.copy_(scores, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return hp.numpy().copy(), hs.numpy().copy()
+
+    def _decode_host_slabs(self, src, dL, slab):
+        """Upload frames [t0, t1) of every clip (one strided 2-D copy per slab) on the copy stream; the compute
+        stream runs the recursion over slab k as soon as its copy has landed and while slab k+1 is in flight."""
+        B, T, S = src.shape
+        n = B * T * S
+        if self._dev_emis is None or self._dev_emis.numel() < n:
+            self._dev_emis = None
+            self._dev_emis = torch.empty(n, dtype=torch.float32, device=self.device)
+        dE = self._dev_emis[:n].view(B, T, S)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        main, cp = torch.cuda.current_stream(), self._copy_stream
+        cp.wait_stream(main)                     # the previous call's kernels may still read the device buffer
+        paths = torch.empty((B, T), dtype=torch.int64, device=self.device)
+        scores = torch.empty((B,), dtype=torch.float32, device=self.device)
+        for t0 in range(0, T, slab):
+            t1 = min(T, t0 + slab)
+            _lib.check(self.lib.vit_upload_frames_f32(_ptr(dE), ctypes.c_void_p(src.data_ptr()), B, T, S, t0, t1,
+                                                      ctypes.c_void_p(cp.cuda_stream)))
+            ev = torch.cuda.Event()
+            ev.record(cp)
+            main.wait_event(ev)
+            self.decode_device(dE, dL, paths, scores, frame_range=(t0, t1), backtrace=(t1 == T))
+        return paths, scores
 
     def decode(self, log_emis, lengths=None):
         """Dispatch on where the emissions live: CUDA tensor -> CUDA tensors, host array -> NumPy arrays."""
