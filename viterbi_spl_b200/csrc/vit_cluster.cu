@@ -271,107 +271,161 @@ cluster_forward_kernel(const float* __restrict__ packedA, const float* __restric
   if (C > 1) cluster_sync();   // no CTA may exit while peers can still address its shared memory
 }
 
-// Lazy-argmax backtrace: one warp per clip.  s_{T-1} = argmax_j delta_{T-1}[j]; then for t = T-1 .. 1
+// Lazy-argmax backtrace over the delta history.  s_{T-1} = argmax_j delta_{T-1}[j]; then for t = T-1 .. 1
 //   s_{t-1} = argmax_i fl32(delta_{t-1}[i] + logA^T[s_t][i])   -- the entry T2[t][s_t] of the reference's table,
 // recomputed with the same fp32 add and the same first-maximum rule (imm/tf_viterbi.py:98-99, 103-107).
-// kBtMaxPerLane: source states per lane held in registers (12 -> S <= 384, 24 -> S <= 768, 48 -> S <= 1536)
-template <int kBtMaxPerLane>
-__global__ void __launch_bounds__(128)
-cluster_backtrace_kernel(const float* __restrict__ logA_T, const float* __restrict__ hist,
-                         const int32_t* __restrict__ lengths, int B, int T_max, int S,
-                         int64_t* __restrict__ paths, float* __restrict__ scores) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= B) return;
-  const int b = warp;
-  const int len = lengths ? lengths[b] : T_max;
-  int64_t* p = paths + (size_t)b * T_max;
-  for (int t = len + lane; t < T_max; t += 32) p[t] = -1;
-  if (len <= 0) {
-    if (lane == 0 && scores) scores[b] = -INFINITY;
-    return;
-  }
-  const float* h = hist + (size_t)b * T_max * S;
-  const int nper = (S + 31) / 32;
+//
+// The walk is a chain of T dependent L2 reads (the logA^T row of the state just found), ~1 us each, so one warp per
+// clip is latency-bound (3.5 ms at 1024 x 3000).  It is parallelised over TIME without changing the result:
+//   pass 1 (speculative): every clip is cut into segments of kBtSeg frames; a warp walks ONE segment downwards from a
+//           guessed state at the segment's top frame e -- argmax_j delta_e[j], the end of the best path into frame e
+//           (for the last segment this is the true s_{T-1}).  s_{t-1} is a function of s_t alone, so the segment's
+//           states are exact from wherever the guess is right, or from wherever the walk MERGES with the true path.
+//   pass 2 (fix-up): a warp per clip goes through the segment boundaries from the top: it steps from the final state
+//           above a boundary into the segment below and, while the result differs from what pass 1 wrote, overwrites
+//           and keeps walking; at the first agreement the rest of the segment is already exact.  Worst case (no
+//           merge) it re-walks everything -- slower, never wrong.
+constexpr int kBtSeg = 128;    // frames per segment (multiple of 32: path stores are whole 256-byte lines)
+constexpr int kBtWarps = 4;
 
-  // s = argmax(T1[-1])
+// one step of the walk: given s_t and delta_{t-1} (registers, lane l holds states l, l+32, ...) -> s_{t-1}
+template <int PER>
+__device__ __forceinline__ int bt_step(const float* __restrict__ logA_T, int S, int s, const float (&d)[PER], int lane) {
+  const float* arow = logA_T + (size_t)s * S;
+  float a[PER];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = lane + 32 * k;
+    a[k] = (i < S) ? __ldg(arow + i) : 0.f;                           // logA^T rows are re-used: L1/L2-resident
+  }
   float best = -INFINITY;
   int arg = 0x7fffffff;
-  {
-    const float* row = h + (size_t)(len - 1) * S;
-    for (int k = 0; k < nper; ++k) {
-      const int i = lane + 32 * k;
-      if (i < S) argmax_combine(best, arg, row[i], i);
-    }
-    warp_argmax(best, arg);
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = lane + 32 * k;
+    if (i < S) argmax_combine(best, arg, __fadd_rn(d[k], a[k]), i);
   }
-  if (lane == 0 && scores) scores[b] = best;
+  warp_argmax(best, arg);
+  return arg;
+}
+
+template <int PER>
+__device__ __forceinline__ void bt_load_row(const float* __restrict__ row, int S, float (&d)[PER], int lane) {
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = lane + 32 * k;
+    d[k] = (i < S) ? ld_global_nc_f32(row + i) : -INFINITY;           // streamed once: keep it out of L1
+  }
+}
+
+template <int PER>
+__global__ void __launch_bounds__(32 * kBtWarps)
+backtrace_segments_kernel(const float* __restrict__ logA_T, const float* __restrict__ hist,
+                          const int32_t* __restrict__ lengths, int B, int T_max, int S, int nseg_max,
+                          int64_t* __restrict__ paths, float* __restrict__ scores) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  // segment-major warp order: the long-latency top segments of all clips are scheduled first
+  const int seg = warp / B, b = warp - seg * B;
+  if (seg >= nseg_max) return;
+  const int len = lengths ? lengths[b] : T_max;
+  int64_t* p = paths + (size_t)b * T_max;
+  const int lo = seg * kBtSeg;
+  // frames past the clip's length are -1; every segment clears its own slice of them
+  for (int t = max(lo, len) + lane; t < min(lo + kBtSeg, T_max); t += 32) p[t] = -1;
+  if (len <= 0) {
+    if (seg == 0 && lane == 0 && scores) scores[b] = -INFINITY;
+    return;
+  }
+  if (lo >= len) return;
+  const int e = min(lo + kBtSeg, len) - 1;                            // top frame of this segment
+  const float* h = hist + (size_t)b * T_max * S;
+
+  // start state: argmax(T1[e]) -- for the last segment this is `s = np.argmax(T1[-1])` (imm/tf_viterbi.py:103)
+  float d[PER];
+  bt_load_row<PER>(h + (size_t)e * S, S, d, lane);
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = lane + 32 * k;
+    if (i < S) argmax_combine(best, arg, d[k], i);
+  }
+  warp_argmax(best, arg);
+  if (e == len - 1 && lane == 0 && scores) scores[b] = best;
   int s = arg;
   int64_t mine = 0;                         // lane l keeps states[t] for t % 32 == l until a full line is ready
-  if (((len - 1) & 31) == lane) mine = s;
-  if (((len - 1) & 31) == 0) { if (lane == 0) p[len - 1] = mine; }
+  if ((e & 31) == lane) mine = s;
+  if ((e & 31) == 0) { if (lane == 0) p[e] = mine; }
 
-  float d[kBtMaxPerLane];
-  if (len >= 2) {
-    const float* row = h + (size_t)(len - 2) * S;
-#pragma unroll
-    for (int k = 0; k < kBtMaxPerLane; ++k) {
-      const int i = lane + 32 * k;
-      d[k] = (i < S) ? row[i] : -INFINITY;
-    }
-  }
-  for (int t = len - 1; t >= 1; --t) {
-    const float* arow = logA_T + (size_t)s * S;
-    float a[kBtMaxPerLane];
-#pragma unroll
-    for (int k = 0; k < kBtMaxPerLane; ++k) {
-      const int i = lane + 32 * k;
-      a[k] = (i < S) ? arow[i] : 0.f;
-    }
+  if (e > lo) bt_load_row<PER>(h + (size_t)(e - 1) * S, S, d, lane);
+  for (int t = e; t > lo; --t) {
     // prefetch delta_{t-2} (independent of s) while the dependent logA^T row is in flight
-    float dn[kBtMaxPerLane];
-    if (t >= 2) {
-      const float* row = h + (size_t)(t - 2) * S;
-#pragma unroll
-      for (int k = 0; k < kBtMaxPerLane; ++k) {
-        const int i = lane + 32 * k;
-        dn[k] = (i < S) ? row[i] : -INFINITY;
-      }
-    }
-    best = -INFINITY;
-    arg = 0x7fffffff;
-#pragma unroll
-    for (int k = 0; k < kBtMaxPerLane; ++k) {
-      const int i = lane + 32 * k;
-      if (i < S) argmax_combine(best, arg, __fadd_rn(d[k], a[k]), i);
-    }
-    warp_argmax(best, arg);
-    s = arg;
+    float dn[PER];
+    if (t - 2 >= lo) bt_load_row<PER>(h + (size_t)(t - 2) * S, S, dn, lane);
+    s = bt_step<PER>(logA_T, S, s, d, lane);
     const int tt = t - 1;
     if ((tt & 31) == lane) mine = s;
     if ((tt & 31) == 0) {
       // states[tt .. tt+31] are complete: one coalesced 256-byte store
-      if (tt + lane < len) p[tt + lane] = mine;
+      if (tt + lane <= e) p[tt + lane] = mine;
     }
 #pragma unroll
-    for (int k = 0; k < kBtMaxPerLane; ++k) d[k] = dn[k];
+    for (int k = 0; k < PER; ++k) d[k] = dn[k];
+  }
+}
+
+template <int PER>
+__global__ void __launch_bounds__(32 * kBtWarps)
+backtrace_fixup_kernel(const float* __restrict__ logA_T, const float* __restrict__ hist,
+                       const int32_t* __restrict__ lengths, int B, int T_max, int S, int64_t* __restrict__ paths) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int len = lengths ? lengths[b] : T_max;
+  if (len <= kBtSeg) return;
+  int64_t* p = paths + (size_t)b * T_max;
+  const float* h = hist + (size_t)b * T_max * S;
+  const int nseg = (len + kBtSeg - 1) / kBtSeg;
+  for (int k = nseg - 2; k >= 0; --k) {
+    int t = (k + 1) * kBtSeg - 1;                                     // top frame of segment k
+    int s_next = (int)p[t + 1];                                       // final (segment k+1 is already exact)
+    while (t >= 0) {
+      float d[PER];
+      bt_load_row<PER>(h + (size_t)t * S, S, d, lane);
+      const int s = bt_step<PER>(logA_T, S, s_next, d, lane);
+      if (s == (int)p[t]) break;                                      // merged: everything below is already exact
+      __syncwarp();
+      if (lane == 0) p[t] = s;
+      __syncwarp();
+      s_next = s;
+      --t;
+    }
   }
 }
 
 // shared with vit_tmem.cu: both forward kernels leave the same fp32 delta history behind
 int launch_hist_backtrace(const float* logA_T, const float* hist, const int32_t* lengths, int B, int T_max, int S,
                           int64_t* paths, float* scores, cudaStream_t stream) {
-  const int warps_per_block = 4;
-  const dim3 grid((B + warps_per_block - 1) / warps_per_block), block(warps_per_block * 32);
-  if (S <= 32 * 12)
-    cluster_backtrace_kernel<12><<<grid, block, 0, stream>>>(logA_T, hist, lengths, B, T_max, S, paths, scores);
-  else if (S <= 32 * 24)
-    cluster_backtrace_kernel<24><<<grid, block, 0, stream>>>(logA_T, hist, lengths, B, T_max, S, paths, scores);
-  else if (S <= 32 * 48)
-    cluster_backtrace_kernel<48><<<grid, block, 0, stream>>>(logA_T, hist, lengths, B, T_max, S, paths, scores);
-  else
-    return VIT_ERR_UNSUPPORTED_ALGO;
-  note_launch();
+  const int nseg_max = (T_max + kBtSeg - 1) / kBtSeg;
+  const long long warps = (long long)B * nseg_max;
+  const dim3 block(kBtWarps * 32);
+  const dim3 grid1((unsigned)((warps + kBtWarps - 1) / kBtWarps)), grid2((B + kBtWarps - 1) / kBtWarps);
+#define VIT_LAUNCH_BT(PER)                                                                                          \
+  do {                                                                                                              \
+    backtrace_segments_kernel<PER><<<grid1, block, 0, stream>>>(logA_T, hist, lengths, B, T_max, S, nseg_max, paths, \
+                                                                scores);                                            \
+    note_launch();                                                                                                  \
+    if (nseg_max > 1) {                                                                                             \
+      backtrace_fixup_kernel<PER><<<grid2, block, 0, stream>>>(logA_T, hist, lengths, B, T_max, S, paths);          \
+      note_launch();                                                                                                \
+    }                                                                                                               \
+  } while (0)
+  if (S <= 32 * 12) VIT_LAUNCH_BT(12);
+  else if (S <= 32 * 24) VIT_LAUNCH_BT(24);
+  else if (S <= 32 * 48) VIT_LAUNCH_BT(48);
+  else return VIT_ERR_UNSUPPORTED_ALGO;
+#undef VIT_LAUNCH_BT
   VIT_CUDA_TRY(cudaGetLastError());
   return VIT_OK;
 }

@@ -255,7 +255,8 @@ tmem_forward_kernel(const float* __restrict__ packedT, const float* __restrict__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tbase = s_tmem_base + ((uint32_t)(Q * 32) << 16);
+  // broadcast from lane 0 so that the compiler keeps the TMEM address in a uniform register (no R2UR per tcgen05.ld)
+  const uint32_t tbase = __shfl_sync(0xffffffffu, s_tmem_base + ((uint32_t)(Q * 32) << 16), 0);
   if (pipe == 0) {
     // the four warps of pipeline 0 fill their TMEM lane quadrant with this CTA's logA^T shard
     const float4* src = reinterpret_cast<const float4*>(packedT + ((size_t)rank * 128 + Q * 32 + lane) * tTmemCols);
