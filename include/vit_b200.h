@@ -121,6 +121,24 @@ int vit_decode_f32_ex(const float* d_logA_T, const float* d_log_pi, const float*
                       int64_t* d_paths, float* d_scores, const vit_decode_opts* opts, void* stream);
 
 /*
+ * Scaled sum-product forward-backward on the same model (north-star item 4).  The reference has NO such pass (its
+ * SoftMaxViterbi classes are max-product decoders, dcnet/softmax_viterbi.py:2488-2674); the semantics are the textbook
+ * scaled recursion on the quantities those classes hold (oracle/fb_oracle.py states them):
+ *   d_A      [S][S]  row-stochastic, row = source state (the matrix viterbi_transition_matrix.dat stores)
+ *   d_pi     [S]     initial distribution                (viterbi_init_probs.dat)
+ *   d_lik    [B][T_max][S]  emission likelihoods b_t >= 0 (SoftMaxViterbi.observation_probs_fn output, probability
+ *                    domain, NOT logged: dcnet/softmax_viterbi.py:2530-2579)
+ *   d_gamma  [B][T_max][S]  out: posterior state marginals gamma_t (0 for frames >= length)
+ *   d_loglik [B]     out: log L = sum_t log c_t (0 for an empty clip); may be NULL
+ * float32 arithmetic; |gamma - float64 oracle| <= 1e-4, log L within 1e-5 relative.  S <= 384 x cluster size limits
+ * as for VIT_ALGO_TMEM (vit_fb_workspace_bytes returns VIT_ERR_UNSUPPORTED_ALGO otherwise).
+ */
+int vit_fb_workspace_bytes(int B, int T_max, int S, size_t* out_bytes);
+int vit_forward_backward_f32(const float* d_A, const float* d_pi, const float* d_lik, const int32_t* d_lengths,
+                             int B, int T_max, int S, void* d_workspace, size_t workspace_bytes,
+                             float* d_gamma, float* d_loglik, void* stream);
+
+/*
  * Host -> device upload of frames [frame_begin, frame_end) of every clip of a [B][T_max][S] float32 batch: one strided
  * 2-D async copy on `stream` (h_log_emis should be page-locked for the copy to be asynchronous).  Together with the
  * frame ranges of vit_decode_f32_ex this lets a host overlap the PCIe transfer of time slab k+1 with the recursion

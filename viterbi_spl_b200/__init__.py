@@ -11,5 +11,6 @@ fallback -- constructing a decoder without the library or without a GPU raises.
 """
 from . import _lib, hmm_params, synth  # noqa: F401
 from .decoder import ViterbiDecoder, decode_batch  # noqa: F401
+from .posterior import ForwardBackward  # noqa: F401
 
 __version__ = '0.1.0'

@@ -14,7 +14,8 @@ ALGO_NAMES = {'auto': ALGO_AUTO, 'backpointer': ALGO_BACKPOINTER, 'cluster': ALG
 
 # every symbol include/vit_b200.h declares (tests/test_abi.py checks the built library exports them all)
 EXPORTS = ['vit_version', 'vit_strerror', 'vit_last_cuda_error', 'vit_launch_count', 'vit_select_algo',
-           'vit_workspace_bytes', 'vit_decode_f32', 'vit_decode_f32_ex', 'vit_upload_frames_f32']
+           'vit_workspace_bytes', 'vit_decode_f32', 'vit_decode_f32_ex', 'vit_upload_frames_f32',
+           'vit_fb_workspace_bytes', 'vit_forward_backward_f32']
 
 
 class DecodeOpts(ctypes.Structure):
@@ -58,6 +59,10 @@ def load():
     L.vit_decode_f32.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp, vp, vp]
     L.vit_decode_f32_ex.restype = ci
     L.vit_decode_f32_ex.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp, vp, ctypes.POINTER(DecodeOpts), vp]
+    L.vit_fb_workspace_bytes.restype = ci
+    L.vit_fb_workspace_bytes.argtypes = [ci, ci, ci, ctypes.POINTER(sz)]
+    L.vit_forward_backward_f32.restype = ci
+    L.vit_forward_backward_f32.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp, vp, vp]
     L.vit_upload_frames_f32.restype = ci
     L.vit_upload_frames_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
     _lib = L

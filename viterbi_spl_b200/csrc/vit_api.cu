@@ -38,6 +38,13 @@ int tmem_decode(const float* logA_T, const float* log_pi, const float* log_emis,
                 float* delta_out, int t_begin, int t_end, bool do_backtrace, cudaEvent_t ev0, cudaEvent_t ev1,
                 cudaStream_t stream);
 
+// vit_fb.cu
+size_t fb_workspace_bytes(int B, int T_max, int S);
+bool fb_supported(int S);
+int fb_run(const float* A, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S,
+           void* workspace, size_t workspace_bytes, float* gamma, float* loglik, cudaEvent_t ev0, cudaEvent_t ev1,
+           cudaStream_t stream);
+
 static int check_shape(int B, int T_max, int S) {
   if (B < 0 || T_max < 1 || S < 1) return VIT_ERR_INVALID_ARGUMENT;
   if (S > 65535) return VIT_ERR_STATES_TOO_MANY;
@@ -135,6 +142,28 @@ int vit_decode_f32(const float* d_logA_T, const float* d_log_pi, const float* d_
                    float* d_scores, void* stream) {
   return vit_decode_f32_ex(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes,
                            d_paths, d_scores, nullptr, stream);
+}
+
+int vit_fb_workspace_bytes(int B, int T_max, int S, size_t* out_bytes) {
+  if (!out_bytes) return VIT_ERR_INVALID_ARGUMENT;
+  int rc = check_shape(B, T_max, S);
+  if (rc != VIT_OK) return rc;
+  if (!fb_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;
+  *out_bytes = fb_workspace_bytes(B, T_max, S);
+  return VIT_OK;
+}
+
+int vit_forward_backward_f32(const float* d_A, const float* d_pi, const float* d_lik, const int32_t* d_lengths, int B,
+                             int T_max, int S, void* d_workspace, size_t workspace_bytes, float* d_gamma,
+                             float* d_loglik, void* stream) {
+  int rc = check_shape(B, T_max, S);
+  if (rc != VIT_OK) return rc;
+  if (!d_A || !d_pi || !d_gamma || (!d_lik && B > 0)) return VIT_ERR_INVALID_ARGUMENT;
+  if (!fb_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;
+  if (!d_workspace) return VIT_ERR_WORKSPACE_TOO_SMALL;
+  if (((uintptr_t)d_workspace & 255u) != 0) return VIT_ERR_MISALIGNED;
+  return fb_run(d_A, d_pi, d_lik, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_gamma, d_loglik, nullptr,
+                nullptr, (cudaStream_t)stream);
 }
 
 int vit_upload_frames_f32(float* d_log_emis, const float* h_log_emis, int B, int T_max, int S, int frame_begin,
