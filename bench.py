@@ -204,6 +204,11 @@ def run_ours(a):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (NCCL's version banner) goes
+    # to stderr instead
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     # CPU baseline first (N=1 only): worker processes are forked before this process creates a CUDA context
     cpu = cpu_baseline(a) if (world == 1 and not a.no_cpu) else None
     if not torch.cuda.is_available():
@@ -340,6 +345,8 @@ def run_ours(a):
     }
     if cpu is not None:
         line['cpu_baseline'] = cpu
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -139,6 +139,28 @@ int vit_forward_backward_f32(const float* d_A, const float* d_pi, const float* d
                              float* d_gamma, float* d_loglik, void* stream);
 
 /*
+ * The step before the decode: acoustic-model logits -> HMM emission table, batched on the GPU.
+ *   model VIT_EMIS_SOFTMAX (0): SoftMaxViterbi.observation_probs_fn, dcnet/softmax_viterbi.py:2508-2579:
+ *       d_logits [B][T][1 + n_bins], column 0 = the unvoiced logit; d_prior [1 + n_bins] = np.roll(ini_probs, 1)
+ *       ("scaled", :2534-2538) or NULL ("unscaled").
+ *   model VIT_EMIS_SHAUN (1): Viterbi.observation_probs_fn, tonet/softmax_priors.py:1741-1786:
+ *       d_logits [B][T][n_bins]; threshold = log(th / (1 - th)) of the voicing threshold (:1705-1706).
+ *   single_side_peak_width: 5 (dcnet/msnet/ftanet/tonet), 16 (jdc), 20 (imm).
+ *   d_out [B][T][n_bins + 1], unvoiced state LAST; out_log != 0 writes log(p + tiny) -- what the decoders take at
+ *   dcnet/softmax_viterbi.py:2650-2653 -- so the table can go straight into vit_decode_f32.
+ * Peak picking is exact; the exp/log values are within 1e-5 relative of NumPy's (not bit-identical: this entry point
+ * is outside the decoder's bit-exact claim).
+ */
+#define VIT_EMIS_SOFTMAX 0
+#define VIT_EMIS_SHAUN 1
+int vit_emissions_f32(const float* d_logits, const float* d_prior, int B, int T, int n_bins, int model,
+                      int single_side_peak_width, float threshold, int out_log, float* d_out, void* stream);
+
+/* The step after the decode (dcnet/softmax_viterbi.py:2427-2431): voiced = state < n_bins,
+ * bins = min(state, n_bins - 1); frames past a clip's length (state -1) give voiced = 0, bins = -1. */
+int vit_voiced_bins(const int64_t* d_states, long long n, int n_bins, uint8_t* d_voiced, int64_t* d_bins, void* stream);
+
+/*
  * Host -> device upload of frames [frame_begin, frame_end) of every clip of a [B][T_max][S] float32 batch: one strided
  * 2-D async copy on `stream` (h_log_emis should be page-locked for the copy to be asynchronous).  Together with the
  * frame ranges of vit_decode_f32_ex this lets a host overlap the PCIe transfer of time slab k+1 with the recursion

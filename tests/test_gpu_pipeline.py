@@ -1,0 +1,87 @@
+"""The steps either side of the hot path on the GPU (vit_emissions_f32, vit_voiced_bins) against goldens produced by the
+reference's own observation_probs_fn / __call__ (tests/golden/make_golden.py).  Peak patterns must be identical; values
+within 1e-5 relative (GPU expf/logf vs NumPy's float32 routines -- this path is outside the bit-exact claim)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from viterbi_spl_b200 import hmm_params
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+TINY = np.finfo(np.float32).tiny
+
+
+@pytest.fixture(scope='module')
+def pl(cuda_lib):
+    assert torch.cuda.is_available()
+    from viterbi_spl_b200 import pipeline
+    return pipeline
+
+
+def close(got, want):
+    assert np.array_equal(got != 0, want != 0), 'peak pattern differs'
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-7), np.abs(got - want).max()
+
+
+@pytest.mark.parametrize('scaled', [0, 1])
+def test_softmax_model_matches_msnet_golden(pl, scaled):
+    m = np.load(os.path.join(GOLD, 'msnet_softmax_viterbi.npz'))
+    ml = np.load(os.path.join(GOLD, 'msnet_logdomain.npz'))
+    logits = torch.as_tensor(m['logits'][None]).cuda()                      # [1, T, 1 + 320], column 0 = unvoiced
+    prior = torch.as_tensor(np.roll(ml['ini_probs'], 1).copy()).cuda() if scaled else None
+    p = pl.emissions_device(logits, 320, pl.SOFTMAX, prior, 5, 0.0, out_log=False)[0].cpu().numpy()
+    close(p, m[f'prob_ts_{scaled}'])
+    lp = pl.emissions_device(logits, 320, pl.SOFTMAX, prior, 5, 0.0, out_log=True)[0].cpu().numpy()
+    assert np.allclose(lp, m[f'log_prob_ts_{scaled}'], rtol=0, atol=2e-5)
+    # decode the GPU-built table: same (voiced, bins) as the reference's end-to-end __call__ on this recording
+    from viterbi_spl_b200 import ViterbiDecoder
+    st, _ = ViterbiDecoder(ml['logA_T'], ml['log_pi']).decode_device(torch.as_tensor(lp[None]).cuda())
+    voiced, bins = pl.voiced_bins_device(st, 320)
+    agree = np.mean((voiced[0].cpu().numpy() == m[f'voiced_{scaled}']) & (bins[0].cpu().numpy() == m[f'bins_{scaled}']))
+    assert agree >= 0.99, agree
+
+
+def test_shaun_model_matches_tonet_golden_and_full_pipeline(pl):
+    b = np.load(os.path.join(GOLD, 'tonet_family_b.npz'))
+    logits = torch.as_tensor(b['logits'][None]).cuda()                      # [1, T, 360]
+    p = pl.emissions_device(logits, 360, pl.SHAUN, None, 5, 0.0, out_log=False)[0].cpu().numpy()      # threshold 0.5 -> logit 0
+    close(p, b['probs_st'].T)
+    assert np.allclose(p.sum(1), 1, atol=1e-5)
+    mp = pl.MelodyPipeline(b['A'], b['pi'], model='shaun', voicing_threshold=0.5)
+    voiced, bins = mp(b['logits'])
+    agree = np.mean((voiced.cpu().numpy() == b['voiced']) & (bins.cpu().numpy() == b['bins']))
+    assert agree >= 0.99, agree
+
+
+@pytest.mark.parametrize('spw,n_bins', [(5, 64), (16, 100), (20, 721), (1, 3)])
+def test_peak_picking_is_exact_with_ties_and_reflect_padding(pl, spw, n_bins):
+    """Quantised logits (many equal neighbours) against the NumPy argmax-of-window rule of
+    find_peaks_all_at_once_np_fn (dcnet/softmax_viterbi.py:2508-2528), restated here for arbitrary width."""
+    rng = np.random.default_rng(spw * 1000 + n_bins)
+    T = 50
+    x = rng.integers(0, 4, size=(T, n_bins)).astype(np.float32)
+    padded = np.pad(x, [(0, 0), (spw, spw)], mode='reflect')
+    want = np.stack([np.argmax(padded[:, k:k + 2 * spw + 1], axis=1) == spw for k in range(n_bins)], axis=1)
+    p = pl.emissions_device(torch.as_tensor(x[None]).cuda(), n_bins, pl.SHAUN, None, spw, 0.0, out_log=False)[0].cpu().numpy()
+    assert np.array_equal(p[:, :n_bins] != 0, want)
+    none = ~want.any(1)
+    assert np.all(p[none, n_bins] == 1)                                     # no peak: E[unvoiced] = 1
+
+
+def test_voiced_bins_and_batched_pipeline(pl):
+    A, pi = hmm_params.synthetic_hmm('tonet')
+    mp = pl.MelodyPipeline(A, pi, model='softmax', scaled=True)
+    g = torch.Generator(device='cuda'); g.manual_seed(1)
+    logits = 2 * torch.randn((5, 90, 361), device='cuda', generator=g)
+    L = torch.as_tensor(np.asarray([90, 0, 17, 1, 90], np.int32)).cuda()
+    voiced, bins = mp(logits, L)
+    assert voiced.shape == (5, 90) and voiced.dtype == torch.bool and bins.dtype == torch.int64
+    E = mp.emissions(logits)
+    st, _ = mp.decoder.decode_device(E, L)
+    st = st.cpu().numpy()
+    assert np.array_equal(voiced.cpu().numpy(), (st >= 0) & (st < 360))
+    assert np.array_equal(bins.cpu().numpy(), np.where(st < 0, -1, np.minimum(st, 359)))
+    assert not voiced[1].any() and (bins[1] == -1).all()

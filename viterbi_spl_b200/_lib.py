@@ -15,7 +15,7 @@ ALGO_NAMES = {'auto': ALGO_AUTO, 'backpointer': ALGO_BACKPOINTER, 'cluster': ALG
 # every symbol include/vit_b200.h declares (tests/test_abi.py checks the built library exports them all)
 EXPORTS = ['vit_version', 'vit_strerror', 'vit_last_cuda_error', 'vit_launch_count', 'vit_select_algo',
            'vit_workspace_bytes', 'vit_decode_f32', 'vit_decode_f32_ex', 'vit_upload_frames_f32',
-           'vit_fb_workspace_bytes', 'vit_forward_backward_f32']
+           'vit_fb_workspace_bytes', 'vit_forward_backward_f32', 'vit_emissions_f32', 'vit_voiced_bins']
 
 
 class DecodeOpts(ctypes.Structure):
@@ -63,6 +63,10 @@ def load():
     L.vit_fb_workspace_bytes.argtypes = [ci, ci, ci, ctypes.POINTER(sz)]
     L.vit_forward_backward_f32.restype = ci
     L.vit_forward_backward_f32.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp, vp, vp]
+    L.vit_emissions_f32.restype = ci
+    L.vit_emissions_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, ctypes.c_float, ci, vp, vp]
+    L.vit_voiced_bins.restype = ci
+    L.vit_voiced_bins.argtypes = [vp, ctypes.c_longlong, ci, vp, vp, vp]
     L.vit_upload_frames_f32.restype = ci
     L.vit_upload_frames_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
     _lib = L

@@ -45,6 +45,11 @@ int fb_run(const float* A, const float* pi, const float* lik, const int32_t* len
            void* workspace, size_t workspace_bytes, float* gamma, float* loglik, cudaEvent_t ev0, cudaEvent_t ev1,
            cudaStream_t stream);
 
+// vit_emis.cu
+int emissions_run(const float* logits, const float* prior, int B, int T, int n_bins, int model, int spw, float threshold,
+                  int out_log, float* out, cudaStream_t stream);
+int voiced_bins_run(const int64_t* states, long long n, int n_bins, uint8_t* voiced, int64_t* bins, cudaStream_t stream);
+
 static int check_shape(int B, int T_max, int S) {
   if (B < 0 || T_max < 1 || S < 1) return VIT_ERR_INVALID_ARGUMENT;
   if (S > 65535) return VIT_ERR_STATES_TOO_MANY;
@@ -164,6 +169,20 @@ int vit_forward_backward_f32(const float* d_A, const float* d_pi, const float* d
   if (((uintptr_t)d_workspace & 255u) != 0) return VIT_ERR_MISALIGNED;
   return fb_run(d_A, d_pi, d_lik, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_gamma, d_loglik, nullptr,
                 nullptr, (cudaStream_t)stream);
+}
+
+int vit_emissions_f32(const float* d_logits, const float* d_prior, int B, int T, int n_bins, int model,
+                      int single_side_peak_width, float threshold, int out_log, float* d_out, void* stream) {
+  if (B < 0 || T < 0 || n_bins < 1 || single_side_peak_width < 0 || single_side_peak_width >= n_bins)
+    return VIT_ERR_INVALID_ARGUMENT;
+  if ((!d_logits || !d_out) && (long long)B * T > 0) return VIT_ERR_INVALID_ARGUMENT;
+  return emissions_run(d_logits, d_prior, B, T, n_bins, model, single_side_peak_width, threshold, out_log, d_out,
+                       (cudaStream_t)stream);
+}
+
+int vit_voiced_bins(const int64_t* d_states, long long n, int n_bins, uint8_t* d_voiced, int64_t* d_bins, void* stream) {
+  if (n < 0 || n_bins < 1 || ((!d_states || !d_voiced || !d_bins) && n > 0)) return VIT_ERR_INVALID_ARGUMENT;
+  return voiced_bins_run(d_states, n, n_bins, d_voiced, d_bins, (cudaStream_t)stream);
 }
 
 int vit_upload_frames_f32(float* d_log_emis, const float* h_log_emis, int B, int T_max, int S, int frame_begin,

@@ -125,7 +125,7 @@ class ViterbiDecoder:
         """log_emis: host float32 array [B, T, S] (NumPy or CPU tensor).  Copies host->device, decodes, copies the
         paths and scores back; returns NumPy (paths int64 [B, T], scores float32 [B]).
 
-        Large batches are uploaded in time slabs of `slab_frames` frames (default: about T/8 once the batch exceeds
+        Large batches are uploaded in time slabs of `slab_frames` frames (default: about T/16 once the batch exceeds
         64 MB) on a copy stream while the recursion over the previous slab runs on the compute stream, so the
         end-to-end time is max(PCIe copy, decode) instead of their sum."""
         E = torch.as_tensor(log_emis)
@@ -141,7 +141,7 @@ class ViterbiDecoder:
             if lengths is not None:
                 dL = torch.as_tensor(np.asarray(lengths, np.int32)).to(self.device)
             if slab_frames is None:
-                slab_frames = T if B * T * S * 4 < (64 << 20) else max(64, -(-T // 8))
+                slab_frames = T if B * T * S * 4 < (64 << 20) else max(64, -(-T // 16))
             if slab_frames >= T or B == 0 or not self.supports_frame_slabs():
                 dE = src.to(self.device, non_blocking=True)
                 paths, scores = self.decode_device(dE, dL)

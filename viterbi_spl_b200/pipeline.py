@@ -1,0 +1,94 @@
+"""Whole post-processing chain on the GPU: acoustic-model logits -> emissions -> Viterbi -> (voiced, bins), batched over
+recordings, nothing round-tripping the host.
+
+It is what the reference's ``SoftMaxViterbi.__call__`` / ``Viterbi.__call__`` do per recording on the CPU
+(dcnet/softmax_viterbi.py:2620-2634, tonet/softmax_priors.py:1825-1839):
+
+    prob = self.observation_probs_fn(logits)       # python loop over frames          -> vit_emissions_f32
+    bins = self.viterbi_librosa_fn(prob)           # log(prob + tiny), recursion      -> vit_decode_f32
+    voiced = bins < n_bins; bins = np.minimum(bins, n_bins - 1)                       -> vit_voiced_bins
+
+The emission values come from the GPU's expf/logf (1e-5 relative to NumPy's, not bit-identical), so unlike the
+``reference_api`` wrappers -- which log on the host and are bit-exact -- a decoded path can differ from the reference
+where two paths are within rounding of each other.  Use ``reference_api`` for bit-exact parity, this for throughput.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, hmm_params
+from .decoder import ViterbiDecoder
+
+SOFTMAX, SHAUN = 0, 1
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def emissions_device(logits, n_bins, model, prior=None, single_side_peak_width=5, threshold=0.0, out_log=True, out=None):
+    """logits: CUDA float32 [B, T, 1 + n_bins] (model SOFTMAX, column 0 = unvoiced) or [B, T, n_bins] (model SHAUN).
+    prior: CUDA float32 [1 + n_bins] = roll(ini_probs, 1) for the "scaled" SoftMax model, else None.
+    Returns the emission table [B, T, n_bins + 1] (unvoiced last), log(p + tiny) if out_log else p."""
+    assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous() and logits.ndim == 3
+    B, T, n_in = logits.shape
+    assert n_in == (n_bins + 1 if model == SOFTMAX else n_bins)
+    if prior is not None:
+        assert model == SOFTMAX and prior.is_cuda and prior.dtype == torch.float32 and prior.shape == (n_bins + 1,)
+    if out is None:
+        out = torch.empty((B, T, n_bins + 1), dtype=torch.float32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        st = torch.cuda.current_stream()
+        _lib.check(_lib.load().vit_emissions_f32(_ptr(logits), _ptr(prior), B, T, n_bins, model, single_side_peak_width,
+                                                 float(threshold), 1 if out_log else 0, _ptr(out),
+                                                 ctypes.c_void_p(st.cuda_stream)))
+    return out
+
+
+def voiced_bins_device(states, n_bins):
+    """states: CUDA int64 [...]; returns (voiced bool [...], bins int64 [...])."""
+    assert states.is_cuda and states.dtype == torch.int64 and states.is_contiguous()
+    voiced = torch.empty(states.shape, dtype=torch.uint8, device=states.device)
+    bins = torch.empty_like(states)
+    with torch.cuda.device(states.device):
+        st = torch.cuda.current_stream()
+        _lib.check(_lib.load().vit_voiced_bins(_ptr(states), states.numel(), n_bins, _ptr(voiced), _ptr(bins),
+                                               ctypes.c_void_p(st.cuda_stream)))
+    return voiced.bool(), bins
+
+
+class MelodyPipeline:
+    """logits [B, T, *] -> (voiced [B, T] bool, bins [B, T] int64) entirely on the GPU.
+
+    model='softmax': logits [B, T, 1 + n_bins] with the unvoiced logit in column 0 (what the tonet/jdc/msnet/ftanet
+    acoustic models emit, tonet/softmax_priors.py:2273-2274; dcnet pads the constant logit(voicing threshold),
+    dcnet/softmax_viterbi.py:2546-2548); scaled=True divides by the prior of each peak state (:2571-2572).
+    model='shaun': logits [B, T, n_bins] and a voicing threshold (probability)."""
+
+    def __init__(self, transition_matrix, ini_probs, model='softmax', scaled=False, voicing_threshold=0.5,
+                 single_side_peak_width=5, device=None, algo='auto'):
+        self.n_bins = len(ini_probs) - 1
+        self.model = {'softmax': SOFTMAX, 'shaun': SHAUN}[model]
+        self.spw = int(single_side_peak_width)
+        self.threshold = float(np.log(voicing_threshold / (1. - voicing_threshold)))         # tonet :1703-1706
+        logA_T, log_pi = hmm_params.log_params(np.asarray(transition_matrix), np.asarray(ini_probs))
+        self.decoder = ViterbiDecoder(logA_T, log_pi, device=device, algo=algo)
+        self.device = self.decoder.device
+        self.prior = None
+        if self.model == SOFTMAX and scaled:
+            self.prior = torch.as_tensor(np.roll(np.asarray(ini_probs, np.float32), 1).copy()).to(self.device)
+
+    def emissions(self, logits, out_log=True):
+        return emissions_device(logits, self.n_bins, self.model, self.prior, self.spw, self.threshold, out_log)
+
+    def __call__(self, logits, lengths=None):
+        logits = torch.as_tensor(logits)
+        squeeze = logits.ndim == 2
+        if squeeze:
+            logits = logits[None]
+        logits = logits.to(self.device, torch.float32).contiguous()
+        E = self.emissions(logits, out_log=True)
+        states, _ = self.decoder.decode_device(E, lengths)
+        voiced, bins = voiced_bins_device(states, self.n_bins)
+        return (voiced[0], bins[0]) if squeeze else (voiced, bins)
