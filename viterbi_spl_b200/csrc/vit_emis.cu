@@ -38,11 +38,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ bool is_peak(const float* x, int n, int k, int spw) {
   const float c = x[k];
   bool ok = true;
-  for (int m = 1; m <= spw; ++m) {
-    int l = k - m, r = k + m;
-    if (l < 0) l = -l;
-    if (r > n - 1) r = 2 * (n - 1) - r;
-    ok = ok && (x[l] < c) && (x[r] <= c);
+  if (k >= spw && k + spw < n) {                                     // interior: no reflection
+    for (int m = 1; m <= spw; ++m) ok = ok && (x[k - m] < c) && (x[k + m] <= c);
+  } else {
+    for (int m = 1; m <= spw; ++m) {
+      int l = k - m, r = k + m;
+      if (l < 0) l = -l;
+      if (r > n - 1) r = 2 * (n - 1) - r;
+      ok = ok && (x[l] < c) && (x[r] <= c);
+    }
   }
   return ok;
 }
@@ -67,16 +71,16 @@ emissions_kernel(const float* __restrict__ logits, const float* __restrict__ pri
     const float* vin = in + (MODEL == 0 ? 1 : 0);
     for (int k = lane; k < n_bins; k += 32) x[k] = vin[k];
     __syncwarp();
-    // pass 1: peaks of my bins, maximum peak logit
+    // pass 1: peak flags of my bins (bit i <-> bin lane + 32 i), maximum peak logit
     float mx = -INFINITY;
-    int n_peaks = 0;
-    for (int k = lane; k < n_bins; k += 32) {
+    uint32_t mask = 0;
+    for (int k = lane, i = 0; k < n_bins; k += 32, ++i) {
       if (is_peak(x, n_bins, k, spw)) {
         mx = fmaxf(mx, x[k]);
-        ++n_peaks;
+        mask |= 1u << i;
       }
     }
-    n_peaks = __reduce_add_sync(0xffffffffu, n_peaks);
+    const int n_peaks = __reduce_add_sync(0xffffffffu, __popc(mask));
     float unv_logit = 0.f;
     if (MODEL == 0) {
       unv_logit = in[0];                                             // column 0 is always a peak (:2521)
@@ -85,8 +89,7 @@ emissions_kernel(const float* __restrict__ logits, const float* __restrict__ pri
     mx = warp_max(mx);
     // pass 2: sum of exp(peak - max)
     float sum = 0.f;
-    for (int k = lane; k < n_bins; k += 32)
-      if (is_peak(x, n_bins, k, spw)) sum += expf(x[k] - mx);
+    for (uint32_t mm = mask; mm; mm &= mm - 1) sum += expf(x[lane + 32 * (__ffs(mm) - 1)] - mx);
     sum = warp_sum(sum);
     float unv_out;
     float scale;                                                     // value of a voiced peak = exp(x - mx) * scale / prior
@@ -111,9 +114,9 @@ emissions_kernel(const float* __restrict__ logits, const float* __restrict__ pri
       }
     }
     // pass 3: write the row (coalesced); non-peaks are exactly 0 -> log(tiny)
-    for (int k = lane; k < n_bins; k += 32) {
+    for (int k = lane, i = 0; k < n_bins; k += 32, ++i) {
       float v = zero_out;
-      if (is_peak(x, n_bins, k, spw)) {
+      if ((mask >> i) & 1u) {
         float p = expf(x[k] - mx);
         if (MODEL == 0) {
           p = p / sum;                                               // np.divide(peak_logits, t) then / priors (:2568-2572)
@@ -146,7 +149,7 @@ int emissions_run(const float* logits, const float* prior, int B, int T, int n_b
   const long long n_frames = (long long)B * T;
   if (n_frames == 0) return VIT_OK;
   const size_t smem = (size_t)kEmisWarps * n_bins * sizeof(float);
-  if (smem > 200 * 1024) return VIT_ERR_UNSUPPORTED_ALGO;
+  if (n_bins > 1024) return VIT_ERR_UNSUPPORTED_ALGO;                 // 32 peak flags per lane
   int num_sms = 148, dev = 0;
   VIT_CUDA_TRY(cudaGetDevice(&dev));
   VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
