@@ -41,7 +41,8 @@ def parse_args():
     ap.add_argument('--clips', type=int, default=1024)
     ap.add_argument('--frames', type=int, default=3000)
     ap.add_argument('--states', type=int, default=361)
-    ap.add_argument('--algo', default='auto')
+    ap.add_argument('--algo', default='dense', help="kernel of the headline 'value': dense (= the tensor-memory "
+                    "max-plus kernel, what the FP32 roofline is about), or auto/tmem/cluster/backpointer/banded")
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='target wall time of the cpu_baseline sample')
@@ -225,7 +226,12 @@ def run_ours(a):
 
     B, T, S = a.clips, a.frames, a.states
     logA_T, log_pi = hmm_for(S)
-    dec = ViterbiDecoder(logA_T, log_pi, device=dev, algo=a.algo)
+    # the headline runs the DENSE max-plus recursion (S^2 cells per frame -- the work BASELINE.json's roofline counts);
+    # the bit-exact structured fast path that algo='auto' would take for this banded matrix is reported separately
+    algo = a.algo
+    if algo == 'dense':
+        algo = 'tmem' if _lib.load().vit_select_algo(a.clips, a.frames, a.states) == _lib.ALGO_TMEM else 'auto'
+    dec = ViterbiDecoder(logA_T, log_pi, device=dev, algo=algo)
     emis = synth.device_dense_softmax(B, T, S, seed=1234 + rank, device=dev)      # 4.4 GB: far larger than the 126 MB L2
     paths = torch.empty((B, T), dtype=torch.int64, device=dev)
     scores = torch.empty((B,), dtype=torch.float32, device=dev)
@@ -260,6 +266,33 @@ def run_ours(a):
     ms_per_step = total_ms / a.steps
     frames_per_rank = B * T
     value = world * frames_per_rank / (ms_per_step * 1e-3)
+
+    # ---- the structured fast path on the same inputs (same results bit for bit, S (2d+2) cells per frame) -----------
+    structured = None
+    if dec.structure.kind == 1 and algo != 'banded':
+        dec_b = ViterbiDecoder(logA_T, log_pi, device=dev, algo='banded')
+        pb = torch.empty_like(paths)
+        sb = torch.empty_like(scores)
+        for _ in range(a.warmup):
+            dec_b.decode_device(emis, None, pb, sb)
+        ev_b = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        b0.record(stream)
+        for k in range(a.steps):
+            dec_b.decode_device(emis, None, pb, sb, forward_events=ev_b[k])
+        b1.record(stream)
+        barrier()
+        tb = torch.tensor([b0.elapsed_time(b1) / a.steps, statistics.mean(x.elapsed_time(y) for (x, y) in ev_b)],
+                          dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        structured = {'algo': 'banded', 'value': world * frames_per_rank / (float(tb[0]) * 1e-3), 'unit': UNIT,
+                      'ms_per_step': float(tb[0]), 'forward_ms': float(tb[1]),
+                      'halfwidth': int(dec.structure.halfwidth), 'dense_state': int(dec.structure.dense_index),
+                      'identical_to_dense': bool(torch.equal(pb, paths) and torch.equal(sb, scores)),
+                      'forward_hbm_GBps': float(B) * T * S * 8 / (float(tb[1]) * 1e-3) / 1e9}
+        del dec_b, pb, sb
 
     # ---- end-to-end through the host API ------------------------------------------------------------------------
     e2e = None
@@ -341,7 +374,7 @@ def run_ours(a):
                    'l2': 'inputs (4.4 GB emissions per step) are far larger than the 126 MB L2',
                    'parallelism': f'{world} x independent clip shards, no data-path collective'},
         'roofline': roofline, 'roofline_hbm': roofline_hbm,
-        'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'parity_vs_oracle': parity,
+        'structured_fast_path': structured, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'parity_vs_oracle': parity,
     }
     if cpu is not None:
         line['cpu_baseline'] = cpu

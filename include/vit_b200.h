@@ -54,8 +54,21 @@ typedef enum vit_algo {
   /* the throughput path: as VIT_ALGO_CLUSTER, but the resident logA^T shard lives in TENSOR MEMORY (tcgen05.ld into
    * registers) so that 2-CTA clusters -- which pack all 148 SMs, 4-CTA clusters strand 16 -- can hold a 361-state
    * shard; 7 clips x 6 targets per thread, two pipelines per CTA.  S <= 384.  Supports frame ranges. */
-  VIT_ALGO_TMEM = 3
+  VIT_ALGO_TMEM = 3,
+  /* bit-exact fast path for structured matrices (Toeplitz band + one dense voiced/unvoiced state + a constant
+   * background, i.e. every matrix the reference's builders produce for S <= 384): S (2d + 2) instead of S^2 cells per
+   * frame.  Needs opts->structure from vit_analyze_structure_f32; VIT_ALGO_AUTO picks it when that says kind = 1. */
+  VIT_ALGO_BANDED = 4
 } vit_algo;
+
+/* Structure of a transition matrix as found by vit_analyze_structure_f32 (see csrc/vit_banded.cu for the proof that
+ * the banded recursion is bit-identical to the dense one). */
+typedef struct vit_structure {
+  int32_t kind;        /* 0 = no exploitable structure (use a dense kernel), 1 = band + background */
+  int32_t halfwidth;   /* d: apart from dense_index, entries that differ from `background` satisfy |i - j| <= d */
+  int32_t dense_index; /* the one state that is a dense source column AND a dense target row (unvoiced), or -1 */
+  float background;    /* c = the minimum entry of logA^T (log(tiny) = -87.33655 for the reference's matrices) */
+} vit_structure;
 
 /* Optional extras for vit_decode_f32_ex (all may be zero/NULL). */
 typedef struct vit_decode_opts {
@@ -74,6 +87,7 @@ typedef struct vit_decode_opts {
   int32_t frame_end;
   int32_t skip_backtrace;
   int32_t reserved2;
+  const vit_structure* structure; /* HOST pointer or NULL: what vit_analyze_structure_f32 found for d_logA_T */
 } vit_decode_opts;
 
 /* Library version (VIT_B200_VERSION of the built library). */
@@ -87,6 +101,11 @@ const char* vit_last_cuda_error(void);
 
 /* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
 uint64_t vit_launch_count(void);
+
+/* Host-side analysis of a transition matrix (h_logA_T is a HOST pointer, [S][S] dst-major as for vit_decode_f32).
+ * Call once per model; pass the result in vit_decode_opts.structure.  Never fails for finite input: a matrix without
+ * the structure gets kind = 0. */
+int vit_analyze_structure_f32(const float* h_logA_T, int S, vit_structure* out);
 
 /* Which algorithm VIT_ALGO_AUTO resolves to for this shape on the current device (a vit_algo), or a negative
  * vit_status. */

@@ -232,6 +232,66 @@ def test_minus_inf_entries_and_all_ties(Decoder):
         assert np.array_equal(p, want_p) and np.array_equal(s, want_s), algo
 
 
+def banded_model(S, d, dense, seed, coarse, background=-87.33655):
+    """logA^T with the structure of the reference's matrices: constant background, band |i-j| <= d of dyadic values,
+    optionally one state that is a dense row and a dense column."""
+    rng = np.random.default_rng(seed)
+    A = np.full((S, S), np.float32(background), np.float32)
+    q = 4.0 if coarse else 1024.0
+    hi = 8 if coarse else 1 << 14
+    for k in range(-d, d + 1):
+        idx = np.arange(max(0, -k), min(S, S - k))
+        A[idx, idx + k] = -(rng.integers(0, hi, size=len(idx)) / q).astype(np.float32)
+    if dense is not None:
+        A[dense, :] = -(rng.integers(0, hi, size=S) / q).astype(np.float32) - 3
+        A[:, dense] = -(rng.integers(0, hi, size=S) / q).astype(np.float32) - 4
+    pi = -(rng.integers(0, hi, size=S) / q).astype(np.float32)
+    return A, pi
+
+
+@pytest.mark.parametrize('S,d,dense,T,B', [(361, 14, 360, 90, 19), (321, 12, 320, 70, 9), (361, 14, 0, 40, 8), (97, 3, 50, 60, 5),
+                                           (384, 14, 383, 25, 17), (5, 1, None, 30, 3), (64, 0, None, 20, 9), (200, 8, 17, 33, 11),
+                                           (130, 13, None, 260, 4), (33, 4, 32, 1, 2)])
+@pytest.mark.parametrize('coarse', [False, True])
+def test_banded_fast_path_is_bit_identical(Decoder, S, d, dense, T, B, coarse):
+    """VIT_ALGO_BANDED (S (2d+2) cells per frame) against the oracle and the dense kernels, including tie-stress
+    values, a -inf background, ragged lengths and dense states in arbitrary positions."""
+    from viterbi_spl_b200 import _lib
+    for bg in (-87.33655, -np.inf):
+        A, pi = banded_model(S, d, dense, seed=S + d + T, coarse=coarse, background=bg)
+        st = _lib.analyze_structure(A)
+        assert st.kind == 1 and st.halfwidth <= d
+        E = synth.batch('tie_stress' if coarse else 'dyadic', B, T, S, seed0=5 + S)
+        L = np.random.default_rng(T).integers(0, T + 1, size=B).astype(np.int32)
+        L[0] = T
+        want_p, want_s = c_oracle.decode_batch_c(A, pi, E, L)
+        dec = Decoder(A, pi, algo='banded')
+        p, s = dec.decode_host(E, L)
+        assert np.array_equal(p, want_p) and np.array_equal(s, want_s), bg
+        pa, sa = Decoder(A, pi, algo='auto').decode_host(E, L)          # auto resolves to the banded kernel here
+        assert np.array_equal(pa, want_p) and np.array_equal(sa, want_s)
+
+
+@pytest.mark.parametrize('state_set', ['dcnet', 'tonet'])
+def test_banded_fast_path_on_the_reference_state_sets(Decoder, state_set):
+    A, pi = hmm_params.synthetic_hmm(state_set)
+    logA_T, log_pi = hmm_params.log_params(A, pi)
+    S = len(pi)
+    for kind in ('dense_softmax', 'sparse_peaks'):
+        E = synth.batch(kind, 21, 300, S, seed0=8)
+        want_p, want_s = c_oracle.decode_batch_c(logA_T, log_pi, E)
+        dE = torch.as_tensor(E).cuda()
+        outs = {}
+        for algo in ('banded', 'tmem'):
+            p, s, = Decoder(logA_T, log_pi, algo=algo).decode_device(dE)
+            outs[algo] = (p.cpu().numpy(), s.cpu().numpy())
+            assert np.array_equal(outs[algo][0], want_p) and np.array_equal(outs[algo][1], want_s), (algo, kind)
+    # a matrix without the structure is refused by the banded kernel and silently takes the dense one under auto
+    Ad, pid = synth.dyadic_hmm(61, seed=3)
+    with pytest.raises(Exception):
+        Decoder(Ad, pid, algo='banded').decode_host(synth.batch('dyadic', 2, 5, 61, seed0=1))
+
+
 @pytest.mark.parametrize('S,T,B,slab', [(361, 64, 40, 16), (361, 50, 9, 7), (97, 33, 6, 1), (321, 40, 15, 39), (722, 30, 16, 11)])
 def test_frame_slabs_resume_from_the_delta_history(Decoder, S, T, B, slab):
     """The recursion run as consecutive frame ranges [t0, t1) (what decode_host does to overlap the upload of the next
@@ -289,7 +349,7 @@ def test_c_abi_error_codes_on_device(cuda_lib):
 # ---- full size: BASELINE.json configuration, size-independent properties ------------------------------------------
 
 def test_full_size_properties(Decoder):
-    """1024 clips x 3000 frames x 361 states: (1) the three independent CUDA implementations agree bit-exactly;
+    """1024 clips x 3000 frames x 361 states: (1) the four independent CUDA implementations agree bit-exactly;
     (2) the returned score equals the fp32 score re-accumulated along the returned path with the reference's operation
     order, T1[t][s_t] = fl(fl(T1[t-1][s_{t-1}] + B[s_t, s_{t-1}]) + E[t][s_t]); (3) a subset equals the CPU oracle;
     (4) decoding is deterministic and invariant to the order of the clips in the batch."""
@@ -303,10 +363,11 @@ def test_full_size_properties(Decoder):
     p2, s2 = dec_b.decode_device(E)
     assert torch.equal(p1, p2) and torch.equal(s1, s2)
     del dec_b, p2, s2
-    dec_k = Decoder(logA_T, log_pi, algo='cluster')
-    p2, s2 = dec_k.decode_device(E)
-    assert torch.equal(p1, p2) and torch.equal(s1, s2)
-    del dec_k, p2, s2
+    for other in ('cluster', 'banded'):
+        dec_k = Decoder(logA_T, log_pi, algo=other)
+        p2, s2 = dec_k.decode_device(E)
+        assert torch.equal(p1, p2) and torch.equal(s1, s2), other
+        del dec_k, p2, s2
     torch.cuda.empty_cache()
     # (2) score along the path, all clips at once, one fused pass per frame
     dA, dpi = torch.as_tensor(logA_T, device=dev), torch.as_tensor(log_pi, device=dev)

@@ -1,0 +1,50 @@
+"""vit_analyze_structure_f32 (host-only entry point of the C ABI: runs without a GPU) on the reference's state sets and
+on hand-made matrices."""
+import numpy as np
+
+from viterbi_spl_b200 import hmm_params
+
+
+def analyze(cuda_lib, A):
+    from viterbi_spl_b200 import _lib
+    st = _lib.analyze_structure(A)
+    return st.kind, st.halfwidth, st.dense_index, st.background
+
+
+def test_reference_state_sets(cuda_lib):
+    log_tiny = np.float32(np.log(np.finfo(np.float32).tiny))
+    for name, S, d in (('dcnet', 321, 12), ('tonet', 361, 14)):
+        A, pi = hmm_params.synthetic_hmm(name)
+        logA_T, _ = hmm_params.log_params(A, pi)
+        kind, hw, di, bg = analyze(cuda_lib, logA_T)
+        assert (kind, hw, di) == (1, d, S - 1) and bg == log_tiny
+    # jdc: band +-40 of 722 states -- too wide / too many states for the register-resident kernel
+    A, pi = hmm_params.synthetic_hmm('jdc')
+    kind, hw, di, bg = analyze(cuda_lib, hmm_params.log_params(A, pi)[0])
+    assert kind == 0 and hw == 40 and di == 721
+    # imm: fully dense
+    A, pi = hmm_params.synthetic_hmm('imm')
+    kind, hw, di, bg = analyze(cuda_lib, hmm_params.log_params(A, pi, add_tiny=False)[0])
+    assert kind == 0
+
+
+def test_hand_made_matrices(cuda_lib):
+    S = 40
+    A = np.full((S, S), -50.0, np.float32)
+    for k in range(-3, 4):
+        idx = np.arange(max(0, -k), min(S, S - k))
+        A[idx, idx + k] = -1.0 - abs(k)
+    assert analyze(cuda_lib, A) == (1, 3, -1, -50.0)
+    B = A.copy()
+    B[7, :] = -2.0
+    B[:, 7] = -3.0
+    assert analyze(cuda_lib, B) == (1, 3, 7, -50.0)
+    C = A.copy()
+    C[0, S - 1] = -1.0                                     # one far entry, not a dense state: the band must cover it
+    assert analyze(cuda_lib, C)[0] == 0
+    D = np.full((S, S), -np.inf, np.float32)
+    D[np.arange(S), np.arange(S)] = 0
+    assert analyze(cuda_lib, D) == (1, 0, -1, -np.inf)
+    E = A.copy()
+    E[3, 3] = np.nan
+    assert analyze(cuda_lib, E)[0] == 0

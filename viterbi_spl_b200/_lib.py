@@ -9,13 +9,21 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libvit_b200.so')
 
 VIT_OK = 0
-ALGO_AUTO, ALGO_BACKPOINTER, ALGO_CLUSTER, ALGO_TMEM = 0, 1, 2, 3
-ALGO_NAMES = {'auto': ALGO_AUTO, 'backpointer': ALGO_BACKPOINTER, 'cluster': ALGO_CLUSTER, 'tmem': ALGO_TMEM}
+ALGO_AUTO, ALGO_BACKPOINTER, ALGO_CLUSTER, ALGO_TMEM, ALGO_BANDED = 0, 1, 2, 3, 4
+ALGO_NAMES = {'auto': ALGO_AUTO, 'backpointer': ALGO_BACKPOINTER, 'cluster': ALGO_CLUSTER, 'tmem': ALGO_TMEM,
+              'banded': ALGO_BANDED}
 
 # every symbol include/vit_b200.h declares (tests/test_abi.py checks the built library exports them all)
 EXPORTS = ['vit_version', 'vit_strerror', 'vit_last_cuda_error', 'vit_launch_count', 'vit_select_algo',
            'vit_workspace_bytes', 'vit_decode_f32', 'vit_decode_f32_ex', 'vit_upload_frames_f32',
-           'vit_fb_workspace_bytes', 'vit_forward_backward_f32', 'vit_emissions_f32', 'vit_voiced_bins']
+           'vit_fb_workspace_bytes', 'vit_forward_backward_f32', 'vit_emissions_f32', 'vit_voiced_bins',
+           'vit_analyze_structure_f32']
+
+
+class Structure(ctypes.Structure):
+    """struct vit_structure"""
+    _fields_ = [('kind', ctypes.c_int32), ('halfwidth', ctypes.c_int32), ('dense_index', ctypes.c_int32),
+                ('background', ctypes.c_float)]
 
 
 class DecodeOpts(ctypes.Structure):
@@ -24,7 +32,8 @@ class DecodeOpts(ctypes.Structure):
                 ('d_backpointers', ctypes.c_void_p), ('d_delta', ctypes.c_void_p),
                 ('ev_forward_begin', ctypes.c_void_p), ('ev_forward_end', ctypes.c_void_p),
                 ('frame_begin', ctypes.c_int32), ('frame_end', ctypes.c_int32),
-                ('skip_backtrace', ctypes.c_int32), ('reserved2', ctypes.c_int32)]
+                ('skip_backtrace', ctypes.c_int32), ('reserved2', ctypes.c_int32),
+                ('structure', ctypes.POINTER(Structure))]
 
 
 class VitError(RuntimeError):
@@ -63,6 +72,8 @@ def load():
     L.vit_fb_workspace_bytes.argtypes = [ci, ci, ci, ctypes.POINTER(sz)]
     L.vit_forward_backward_f32.restype = ci
     L.vit_forward_backward_f32.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp, vp, vp]
+    L.vit_analyze_structure_f32.restype = ci
+    L.vit_analyze_structure_f32.argtypes = [vp, ci, ctypes.POINTER(Structure)]
     L.vit_emissions_f32.restype = ci
     L.vit_emissions_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, ctypes.c_float, ci, vp, vp]
     L.vit_voiced_bins.restype = ci
@@ -86,6 +97,15 @@ def workspace_bytes(B, T_max, S, algo=ALGO_AUTO):
     out = ctypes.c_size_t(0)
     check(load().vit_workspace_bytes(int(B), int(T_max), int(S), int(algo), ctypes.byref(out)))
     return int(out.value)
+
+
+def analyze_structure(logA_T):
+    """vit_analyze_structure_f32 on a host float32 [S, S] array; returns a Structure."""
+    import numpy as np
+    A = np.ascontiguousarray(logA_T, np.float32)
+    st = Structure()
+    check(load().vit_analyze_structure_f32(A.ctypes.data_as(ctypes.c_void_p), int(A.shape[0]), ctypes.byref(st)))
+    return st
 
 
 def launch_count():

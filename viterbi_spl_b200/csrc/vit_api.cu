@@ -50,6 +50,14 @@ int emissions_run(const float* logits, const float* prior, int B, int T, int n_b
                   int out_log, float* out, cudaStream_t stream);
 int voiced_bins_run(const int64_t* states, long long n, int n_bins, uint8_t* voiced, int64_t* bins, cudaStream_t stream);
 
+// vit_banded.cu
+bool banded_supported(int S, const vit_structure* st);
+size_t banded_workspace_bytes(int B, int T_max, int S);
+int banded_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
+                  int T_max, int S, const vit_structure* st, void* workspace, size_t workspace_bytes, int64_t* paths,
+                  float* scores, float* delta_out, cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t stream);
+int analyze_structure(const float* A, int S, vit_structure* out);
+
 static int check_shape(int B, int T_max, int S) {
   if (B < 0 || T_max < 1 || S < 1) return VIT_ERR_INVALID_ARGUMENT;
   if (S > 65535) return VIT_ERR_STATES_TOO_MANY;
@@ -101,6 +109,10 @@ int vit_workspace_bytes(int B, int T_max, int S, int algo, size_t* out_bytes) {
   if (!out_bytes) return VIT_ERR_INVALID_ARGUMENT;
   int rc = check_shape(B, T_max, S);
   if (rc != VIT_OK) return rc;
+  if (algo == VIT_ALGO_BANDED) {   // whether the matrix qualifies is decided at decode time from opts->structure
+    *out_bytes = banded_workspace_bytes(B, T_max, S);
+    return VIT_OK;
+  }
   int a = resolve_algo(algo, S, false);
   if (a < 0) return a;
   *out_bytes = (a == VIT_ALGO_TMEM)      ? tmem_workspace_bytes(B, T_max, S)
@@ -120,7 +132,16 @@ int vit_decode_f32_ex(const float* d_logA_T, const float* d_log_pi, const float*
   const int algo_req = opts ? opts->algo : VIT_ALGO_AUTO;
   uint16_t* bp_out = opts ? opts->d_backpointers : nullptr;
   float* delta_out = opts ? opts->d_delta : nullptr;
-  const int algo = resolve_algo(algo_req, S, bp_out != nullptr);
+  int algo;
+  const vit_structure* structure = opts ? opts->structure : nullptr;
+  const bool whole = !opts || ((opts->frame_begin == 0) && (opts->frame_end <= 0 || opts->frame_end == T_max) &&
+                               opts->skip_backtrace == 0);
+  if (algo_req == VIT_ALGO_BANDED)
+    algo = (banded_supported(S, structure) && whole && !bp_out) ? (int)VIT_ALGO_BANDED : (int)VIT_ERR_UNSUPPORTED_ALGO;
+  else if (algo_req == VIT_ALGO_AUTO && whole && !bp_out && banded_supported(S, structure))
+    algo = VIT_ALGO_BANDED;
+  else
+    algo = resolve_algo(algo_req, S, bp_out != nullptr);
   if (algo < 0) return algo;
   if (!d_workspace) return VIT_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t st = (cudaStream_t)stream;
@@ -129,6 +150,9 @@ int vit_decode_f32_ex(const float* d_logA_T, const float* d_log_pi, const float*
   const int f_begin = opts ? opts->frame_begin : 0;
   const int f_end = (opts && opts->frame_end > 0) ? opts->frame_end : T_max;
   const bool skip_bt = opts && opts->skip_backtrace != 0;
+  if (algo == VIT_ALGO_BANDED)
+    return banded_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, structure, d_workspace,
+                         workspace_bytes, d_paths, d_scores, delta_out, ev0, ev1, st);
   if (algo == VIT_ALGO_TMEM) {
     // bit 3 of the S check: the shared lazy-argmax backtrace handles S <= 384, which is also the TMEM plan's limit
     return tmem_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_paths,
@@ -183,6 +207,11 @@ int vit_emissions_f32(const float* d_logits, const float* d_prior, int B, int T,
 int vit_voiced_bins(const int64_t* d_states, long long n, int n_bins, uint8_t* d_voiced, int64_t* d_bins, void* stream) {
   if (n < 0 || n_bins < 1 || ((!d_states || !d_voiced || !d_bins) && n > 0)) return VIT_ERR_INVALID_ARGUMENT;
   return voiced_bins_run(d_states, n, n_bins, d_voiced, d_bins, (cudaStream_t)stream);
+}
+
+int vit_analyze_structure_f32(const float* h_logA_T, int S, vit_structure* out) {
+  if (!h_logA_T || !out || S < 1) return VIT_ERR_INVALID_ARGUMENT;
+  return analyze_structure(h_logA_T, S, out);
 }
 
 int vit_upload_frames_f32(float* d_log_emis, const float* h_log_emis, int B, int T_max, int S, int frame_begin,

@@ -1,0 +1,334 @@
+// VIT_ALGO_BANDED -- bit-exact fast path for STRUCTURED transition matrices.
+//
+// Every HMM the reference builds with viterbi_transition_matrix.py / viterbi_transition_post_processing.py is a Toeplitz
+// band (+-d_max pitch bins: 12 dcnet, 14 tonet/ftanet) embedded in a voiced/unvoiced switch
+// (dcnet/viterbi_transition_matrix.py:81-98): outside the band the probabilities are exactly 0, so in the log domain
+// every such entry is the SAME constant c = log(0 + tiny) = -87.33655 (dcnet/softmax_viterbi.py:2459-2462); only the
+// unvoiced state is a dense source column and a dense target row.  With c = the minimum entry of logA^T,
+//
+//     max_i fl(delta_i + a_ji)  =  max(  max_{i in N(j)} fl(delta_i + a_ji),   fl(max_i delta_i + c)  ),
+//
+// N(j) = the entries of row j that differ from c.  Proof: fl32 addition of a constant is monotone, so
+// max_i fl(delta_i + c) = fl(max_i delta_i + c) covers every background entry, and for i in N(j), a_ji >= c gives
+// fl(delta_i + c) <= fl(delta_i + a_ji), so the extra terms never exceed the true maximum.  The recursion value -- hence
+// the delta history, hence the lazily resolved argmax of the backtrace (which still reads the DENSE matrix) -- is
+// bit-identical to the dense kernels', at S (2d + 2) instead of S^2 cells per frame: 11.6x less work at S = 361.
+//
+// The structure is detected once on the host (vit_analyze_structure_f32) and passed in; a matrix without it (the dense
+// imm matrix, imm/transition_matrix.py:4-31) simply takes the dense tensor-memory kernel.
+//
+// Kernel: no clusters, no exchange -- one CTA per SM owns 8 clips for all T steps.  4 independent pipelines of 3 warps
+// (2 clips each, named barriers).  A thread owns 4 consecutive targets and keeps their 4 x (2d+1) band entries in
+// REGISTERS for the whole kernel; its window of delta_{t-1} (4 + 2d values per clip) is 8-9 aligned LDS.128 at
+// compile-time offsets, its 4 results one STS.128.  The dense target row
+// (unvoiced) is split over the 3 warps of a pipeline; its value and max_i delta_i travel as per-warp partials in shared
+// memory and are combined by every thread after the step's single barrier.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "vit_common.cuh"
+
+namespace vit {
+
+constexpr int bNJ = 4;                     // consecutive targets per thread
+constexpr int bCPT = 2;                    // clips per thread
+constexpr int bCS = 4;                     // pipelines (clip groups) per CTA
+constexpr int bMB = bCPT * bCS;            // 8 clips per CTA
+constexpr int bTGW = 3;                    // warps per pipeline: 96 target groups x 4 = 384 targets
+constexpr int bPipeThreads = 32 * bTGW;    // 96
+constexpr int bThreads = bPipeThreads * bCS;
+constexpr int bMaxS = 32 * bTGW * bNJ;     // 384
+// a delta row in shared memory: state i lives at float index i + DP, DP = the band half-width rounded up to a multiple
+// of 4, so that the 4 targets of a thread are one aligned float4 and its window is a run of aligned float4s.
+// 4 * 95 (last target group) + 36 (widest window) = 416 floats cover every thread's accesses for any S <= 384.
+constexpr int bRowLen = 416;
+
+__device__ __forceinline__ void bpipe_bar_sync(int cs) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + cs), "n"(bPipeThreads) : "memory");
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+
+template <int D>
+__global__ void __launch_bounds__(bThreads, 1)
+banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict__ log_pi,
+                      const float* __restrict__ log_emis, const int32_t* __restrict__ lengths, int B, int T_max, int S,
+                      int jd, float cbg, float* __restrict__ hist) {
+  constexpr int W = 2 * D + 1;
+  constexpr int DP = (D + 3) / 4 * 4;
+  constexpr int U0 = DP - D;                         // window element of cell (r, n) = w[U0 + r + n]
+  constexpr int NW4 = (U0 + W - 1 + bNJ + 3) / 4;    // float4s in a thread's window
+  __shared__ __align__(16) float s_delta[bCS][2][bCPT][bRowLen];
+  __shared__ float s_partM[bCS][2][bTGW][bCPT];
+  __shared__ float s_partD[bCS][2][bTGW][bCPT];
+  __shared__ int s_len[bMB];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cs = warp / bTGW, tgw = warp - cs * bTGW;
+  const int tg = tgw * 32 + lane;
+  const int j0 = bNJ * tg;
+
+  // ---- one-time: my band entries -> registers; dense-column and dense-row entries --------------------------------
+  // a[n][r] = logA^T[j0+n][j0+n + r - D]; entries that fall outside the matrix, on the dense state's row or on the
+  // dense state's column are -inf (the dense column has its own term, the dense row its own code)
+  float a[bNJ][W], acol[bNJ], arow[4];
+#pragma unroll
+  for (int n = 0; n < bNJ; ++n) {
+    const int j = j0 + n;
+    const bool jok = j < S && j != jd;
+#pragma unroll
+    for (int r = 0; r < W; ++r) {
+      const int i = j + r - D;
+      a[n][r] = (jok && i >= 0 && i < S && i != jd) ? logA_T[(size_t)j * S + i] : -INFINITY;
+    }
+    acol[n] = (jok && jd >= 0) ? logA_T[(size_t)j * S + jd] : -INFINITY;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = tgw * 128 + lane + 32 * k;
+    arow[k] = (jd >= 0 && i < S) ? logA_T[(size_t)jd * S + i] : -INFINITY;
+  }
+  bool jn_ok[bNJ];
+#pragma unroll
+  for (int n = 0; n < bNJ; ++n) jn_ok[n] = (j0 + n) < S && (j0 + n) != jd;
+  const long long hist_delta = reinterpret_cast<const char*>(hist) - reinterpret_cast<const char*>(log_emis);
+
+  for (int seq0 = blockIdx.x * bMB; seq0 < B; seq0 += gridDim.x * bMB) {
+    __syncthreads();
+    if (tid < bMB) {
+      const int b = seq0 + tid;
+      s_len[tid] = b < B ? (lengths ? lengths[b] : T_max) : 0;
+    }
+    // (re-)arm the delta rows: pads, out-of-range states and the dense state's slot stay -inf for the whole sub-batch
+    for (int x = tid; x < bCS * 2 * bCPT * bRowLen; x += bThreads) (&s_delta[0][0][0][0])[x] = -INFINITY;
+    __syncthreads();
+    const int c0 = cs * bCPT;
+    int len[bCPT];
+#pragma unroll
+    for (int c = 0; c < bCPT; ++c) len[c] = s_len[c0 + c];
+    const int maxlen = max(len[0], len[1]);
+    // address of logE[clip][t][j0], advanced one frame per step; the history sits at a fixed distance
+    const float* pe[bCPT];
+#pragma unroll
+    for (int c = 0; c < bCPT; ++c) pe[c] = log_emis + (size_t)(seq0 + c0 + c) * T_max * S + j0;
+    const int jd_off = jd - j0;                              // logE[..][jd] relative to pe[c]
+
+    float ed_prev[bCPT] = {0.f, 0.f};                        // logE[t-1][jd] of my clips
+    for (int t = 0; t < maxlen; ++t) {
+      const int buf = t & 1;
+      // keep the two running pointers in registers (ptxas would otherwise re-derive the 64-bit address of every load)
+      asm volatile("" : "+l"(pe[0]), "+l"(pe[1]));
+      bool live[bCPT];
+#pragma unroll
+      for (int c = 0; c < bCPT; ++c) live[c] = t < len[c];
+      // this step's emissions: issued first, used last.  The dense state's emission is fetched by one lane per warp.
+      float e[bCPT][bNJ], ed[bCPT];
+#pragma unroll
+      for (int c = 0; c < bCPT; ++c) {
+        // a step is shorter than an HBM round trip: pull the lines of frame t + 4 into L2 now (one lane per 128 B)
+        if ((lane & 7) == 0 && t + 4 < len[c]) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe[c] + 4 * (size_t)S));
+#pragma unroll
+        for (int n = 0; n < bNJ; ++n) e[c][n] = (live[c] && jn_ok[n]) ? __ldg(pe[c] + n) : 0.f;
+        ed[c] = (lane == 0 && live[c] && jd >= 0) ? __ldg(pe[c] + jd_off) : 0.f;
+      }
+
+      float acc[bCPT][bNJ], pd[bCPT], xd[bCPT];
+      if (t == 0) {
+        // T1[0] = log_pi + logE[0]                                                              (imm/tf_viterbi.py:94)
+#pragma unroll
+        for (int c = 0; c < bCPT; ++c) {
+#pragma unroll
+          for (int n = 0; n < bNJ; ++n) acc[c][n] = jn_ok[n] ? log_pi[j0 + n] : -INFINITY;
+          pd[c] = jd >= 0 ? log_pi[jd] : -INFINITY;
+          xd[c] = -INFINITY;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < bCPT; ++c) {
+          const float* prev = s_delta[cs][buf ^ 1][c];
+          // combine the per-warp partials of step t-1: delta_{t-1}[jd] and max_i delta_{t-1}[i]
+          const float* pm = &s_partM[cs][buf ^ 1][0][c];
+          const float* pdd = &s_partD[cs][buf ^ 1][0][c];
+          float dm = fmaxf(fmaxf(pm[0], pm[bCPT]), pm[2 * bCPT]);
+          xd[c] = (jd >= 0) ? __fadd_rn(fmaxf(fmaxf(pdd[0], pdd[bCPT]), pdd[2 * bCPT]), ed_prev[c]) : -INFINITY;
+          dm = fmaxf(dm, xd[c]);
+          if (jd >= 0 && tgw == 0 && lane == 0 && t - 1 < len[c])
+            st_global_cs_f32(hist + ((size_t)(seq0 + c0 + c) * T_max + (t - 1)) * S + jd, xd[c]);
+          // background term fl(max_i delta_i + c) and the dense source column
+          const float bg = __fadd_rn(dm, cbg);
+#pragma unroll
+          for (int n = 0; n < bNJ; ++n) acc[c][n] = fmaxf(bg, __fadd_rn(xd[c], acol[n]));
+          // the band: my window of delta_{t-1} is NW4 aligned float4s starting at my own targets' slot.  One float4 at
+          // a time, applied to every (offset r, target n) cell that reads it: only 4 window values are ever live
+          const float4* row4 = reinterpret_cast<const float4*>(prev) + tg;
+#pragma unroll
+          for (int m = 0; m < NW4; ++m) {
+            const float4 v = row4[m];
+            const float wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+              for (int n = 0; n < bNJ; ++n) {
+                const int r = 4 * m + k - U0 - n;                    // cell (r, n) reads window element U0 + r + n
+                if (r >= 0 && r < W) acc[c][n] = fmaxf(acc[c][n], __fadd_rn(wv[k], a[n][r]));
+              }
+          }
+          // my share of the dense target row: sources tgw*128 + lane + 32 k
+          float m = -INFINITY;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = tgw * 128 + lane + 32 * k;
+            float dv = (i < S) ? prev[i + DP] : -INFINITY;
+            if (i == jd) dv = xd[c];
+            m = fmaxf(m, __fadd_rn(dv, arow[k]));
+          }
+          pd[c] = m;
+        }
+      }
+
+      // T1[t][j] = max + logE[t][j]                                                              (:100)
+      float pm[bCPT];
+#pragma unroll
+      for (int c = 0; c < bCPT; ++c) {
+        float v[bNJ];
+        float mloc = -INFINITY;
+#pragma unroll
+        for (int n = 0; n < bNJ; ++n) {
+          v[n] = jn_ok[n] ? __fadd_rn(acc[c][n], e[c][n]) : -INFINITY;
+          if (live[c] && jn_ok[n])
+            st_global_cs_f32(reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<float*>(pe[c])) + hist_delta) + n, v[n]);
+          mloc = fmaxf(mloc, v[n]);
+        }
+        // one aligned float4 (slots of non-existent / dense targets get -inf, which is what they must hold)
+        reinterpret_cast<float4*>(s_delta[cs][buf][c] + DP)[tg] = make_float4(v[0], v[1], v[2], v[3]);
+        pm[c] = warp_max_f(mloc);
+        pd[c] = warp_max_f(pd[c]);
+        ed[c] = __shfl_sync(0xffffffffu, ed[c], 0);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < bCPT; ++c) {
+          s_partM[cs][buf][tgw][c] = pm[c];
+          s_partD[cs][buf][tgw][c] = pd[c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < bCPT; ++c) {
+        ed_prev[c] = ed[c];
+        pe[c] += S;
+      }
+      bpipe_bar_sync(cs);
+    }
+    // the dense state's value of the last frame
+    if (jd >= 0 && maxlen > 0 && tgw == 0 && lane == 0) {
+      const int buf = (maxlen - 1) & 1;
+#pragma unroll
+      for (int c = 0; c < bCPT; ++c) {
+        if (len[c] == maxlen) {
+          const float* pdd = &s_partD[cs][buf][0][c];
+          const float x = __fadd_rn(fmaxf(fmaxf(pdd[0], pdd[bCPT]), pdd[2 * bCPT]), ed_prev[c]);
+          st_global_cs_f32(hist + ((size_t)(seq0 + c0 + c) * T_max + (maxlen - 1)) * S + jd, x);
+        }
+      }
+    }
+  }
+}
+
+// vit_cluster.cu
+int launch_hist_backtrace(const float* logA_T, const float* hist, const int32_t* lengths, int B, int T_max, int S,
+                          int64_t* paths, float* scores, cudaStream_t stream);
+
+static int banded_template_D(int d) {
+  const int opts[] = {4, 8, 12, 14};
+  for (int o : opts) if (d <= o) return o;
+  return -1;
+}
+
+bool banded_supported(int S, const vit_structure* st) {
+  if (!st || st->kind != 1) return false;
+  if (S > bMaxS || S < 2) return false;
+  if (st->dense_index < -1 || st->dense_index >= S) return false;
+  return banded_template_D(st->halfwidth) > 0;
+}
+
+size_t banded_workspace_bytes(int B, int T_max, int S) {
+  return align_up((size_t)B * T_max * S * sizeof(float), 256);                   // delta history (T1 table)
+}
+
+int banded_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
+                  int T_max, int S, const vit_structure* st, void* workspace, size_t workspace_bytes, int64_t* paths,
+                  float* scores, float* delta_out, cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t stream) {
+  if (!banded_supported(S, st)) return VIT_ERR_UNSUPPORTED_ALGO;
+  if (!delta_out && workspace_bytes < banded_workspace_bytes(B, T_max, S)) return VIT_ERR_WORKSPACE_TOO_SMALL;
+  if (B == 0) return VIT_OK;
+  float* hist = delta_out ? delta_out : (float*)workspace;
+  const int D = banded_template_D(st->halfwidth);
+  int num_sms = 148, dev = 0;
+  VIT_CUDA_TRY(cudaGetDevice(&dev));
+  VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  const int want = (B + bMB - 1) / bMB;
+  const int grid = want < num_sms ? want : num_sms;
+  if (ev0) VIT_CUDA_TRY(cudaEventRecord(ev0, stream));
+#define VIT_BANDED_CASE(DD)                                                                                          \
+  case DD: {                                                                                                         \
+    banded_forward_kernel<DD><<<grid, bThreads, 0, stream>>>(logA_T, log_pi, log_emis, lengths, B, T_max, S,         \
+                                                              st->dense_index, st->background, hist);               \
+  } break;
+  switch (D) {
+    VIT_BANDED_CASE(4) VIT_BANDED_CASE(8) VIT_BANDED_CASE(12) VIT_BANDED_CASE(14)
+    default: return VIT_ERR_UNSUPPORTED_ALGO;
+  }
+#undef VIT_BANDED_CASE
+  note_launch();
+  VIT_CUDA_TRY(cudaGetLastError());
+  if (ev1) VIT_CUDA_TRY(cudaEventRecord(ev1, stream));
+  return launch_hist_backtrace(logA_T, hist, lengths, B, T_max, S, paths, scores, stream);
+}
+
+// Host-side structure analysis (h_logA_T is a HOST pointer).  kind = 1 iff, apart from at most one state that is both
+// a dense source column and a dense target row, every entry that differs from the minimum entry c lies within
+// |i - j| <= halfwidth and the band is narrow enough for the register-resident kernel.
+int analyze_structure(const float* A, int S, vit_structure* out) {
+  out->kind = 0;
+  out->halfwidth = 0;
+  out->dense_index = -1;
+  out->background = 0.f;
+  if (S < 2) return VIT_OK;
+  float c = A[0];
+  for (size_t x = 0; x < (size_t)S * S; ++x) {
+    if (A[x] != A[x]) return VIT_OK;                       // NaN: no structure claimed
+    c = std::min(c, A[x]);
+  }
+  std::vector<int> cnt_row(S, 0), cnt_col(S, 0);
+  for (int j = 0; j < S; ++j)
+    for (int i = 0; i < S; ++i)
+      if (A[(size_t)j * S + i] != c) { ++cnt_row[j]; ++cnt_col[i]; }
+  // candidate dense state: the one with the fullest row + column
+  int dense = -1, best = 0;
+  for (int s = 0; s < S; ++s) {
+    const int v = cnt_row[s] + cnt_col[s];
+    if (v > best) { best = v; dense = s; }
+  }
+  int d_with = 0, d_without = 0;
+  for (int j = 0; j < S; ++j)
+    for (int i = 0; i < S; ++i)
+      if (A[(size_t)j * S + i] != c) {
+        const int d = std::abs(i - j);
+        d_without = std::max(d_without, d);
+        if (i != dense && j != dense) d_with = std::max(d_with, d);
+      }
+  int d = d_without, di = -1;
+  if (d_with < d_without) { d = d_with; di = dense; }
+  out->background = c;
+  out->halfwidth = d;
+  out->dense_index = di;
+  out->kind = (S <= bMaxS && banded_template_D(d) > 0) ? 1 : 0;
+  return VIT_OK;
+}
+
+}  // namespace vit

@@ -42,6 +42,9 @@ class ViterbiDecoder:
         self.S = int(A.shape[0])
         assert pi.shape == (self.S,), 'log_prob_init must be [S]'
         assert not bool(torch.isnan(A).any()) and not bool(torch.isnan(pi).any()), 'parameters contain NaN'
+        # band + background structure of the matrix (every matrix the reference's builders produce has it): unlocks the
+        # bit-exact VIT_ALGO_BANDED fast path under algo='auto'
+        self.structure = _lib.analyze_structure(A.detach().cpu().numpy())
         self.logA_T = A.to(self.device).contiguous()
         self.log_pi = pi.to(self.device).contiguous()
         self.algo = _lib.ALGO_NAMES[algo] if isinstance(algo, str) else int(algo)
@@ -79,7 +82,7 @@ class ViterbiDecoder:
                 if scores is None:
                     scores = torch.empty((B,), dtype=torch.float32, device=self.device)
                 algo = _lib.ALGO_BACKPOINTER if want_tables else self.algo
-                ws = self._workspace(_lib.workspace_bytes(B, T, S, algo))
+                ws = self._workspace(_lib.workspace_bytes(B, T, S, algo))      # (banded needs no more than auto's choice)
                 opts = _lib.DecodeOpts(algo=algo)
                 T1 = T2 = None
                 if want_tables:
@@ -97,6 +100,8 @@ class ViterbiDecoder:
                     opts.frame_begin, opts.frame_end = int(frame_range[0]), int(frame_range[1])
                     assert 0 <= opts.frame_begin < opts.frame_end <= T, 'frame_range must be a non-empty range in [0, T]'
                 opts.skip_backtrace = 0 if backtrace else 1
+                if algo in (_lib.ALGO_AUTO, _lib.ALGO_BANDED):
+                    opts.structure = ctypes.pointer(self.structure)
                 rc = self.lib.vit_decode_f32_ex(_ptr(self.logA_T), _ptr(self.log_pi), _ptr(log_emis), _ptr(lengths),
                                                 B, T, S, _ptr(ws), ws.numel(), _ptr(paths), _ptr(scores),
                                                 ctypes.byref(opts), ctypes.c_void_p(st.cuda_stream))
