@@ -55,13 +55,20 @@ __device__ __forceinline__ bool is_peak(const float* x, int n, int k, int spw) {
 //                    order as np.roll(ini_probs, 1) (dcnet/softmax_viterbi.py:2534-2538), or NULL for "unscaled".
 // model 1 (SHAUN)  : logits [B][T][n_bins]; threshold = logit(voicing threshold); p = 0.8, scale = 2 as in the reference.
 // out [B][T][n_bins + 1], unvoiced LAST (the np.roll(-1) at :2577; the shaun model writes it there directly).
-template <int MODEL>
+// SPW5: single_side_peak_width == 5 (dcnet / msnet / ftanet / tonet) takes the fast peak test: the frame is stored with
+// its reflect padding materialised, window maxima of width 2 and 4 are built by doubling, and
+//   left  max = max(m4[p-5], x[p-1]),  right max = max(m4[p+1], x[p+5])        (p = padded index of the bin)
+// -- 11 shared-memory accesses per bin instead of 21.  Any other width uses the direct neighbour scan.
+template <int MODEL, bool SPW5>
 __global__ void __launch_bounds__(32 * kEmisWarps)
 emissions_kernel(const float* __restrict__ logits, const float* __restrict__ prior, long long n_frames, int n_bins, int spw,
                  float threshold, int out_log, float* __restrict__ out) {
-  extern __shared__ float s_x[];                                     // [kEmisWarps][n_bins]
+  extern __shared__ float s_x[];                                     // [kEmisWarps][3][n_bins + 16] (SPW5) or [.][n_bins]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float* x = s_x + (size_t)w * n_bins;
+  const int np = n_bins + 16;                                        // padded row: 5 + n_bins + 5, rounded up
+  float* x = SPW5 ? s_x + (size_t)w * 3 * np + 5 : s_x + (size_t)w * n_bins;   // x[k] = logit of bin k; x[-5 .. n+4] valid
+  float* m2 = s_x + (size_t)w * 3 * np + np + 5;
+  float* m4 = s_x + (size_t)w * 3 * np + 2 * np + 5;
   const int n_in = MODEL == 0 ? n_bins + 1 : n_bins;
   const int S = n_bins + 1;
   const float zero_out = out_log ? logf(kTinyF) : 0.f;               // log(0 + tiny) = -87.33655
@@ -70,12 +77,30 @@ emissions_kernel(const float* __restrict__ logits, const float* __restrict__ pri
     float* o = out + f * S;
     const float* vin = in + (MODEL == 0 ? 1 : 0);
     for (int k = lane; k < n_bins; k += 32) x[k] = vin[k];
+    if (SPW5) {
+      __syncwarp();
+      if (lane < 5) {                                                // np.pad(mode='reflect'): -m -> m, n-1+m -> n-1-m
+        x[-1 - lane] = x[1 + lane];
+        x[n_bins + lane] = x[n_bins - 2 - lane];
+      }
+      __syncwarp();
+      for (int k = lane - 5; k < n_bins + 4; k += 32) m2[k] = fmaxf(x[k], x[k + 1]);          // max of x[k .. k+1]
+      __syncwarp();
+      for (int k = lane - 5; k < n_bins + 2; k += 32) m4[k] = fmaxf(m2[k], m2[k + 2]);         // max of x[k .. k+3]
+    }
     __syncwarp();
     // pass 1: peak flags of my bins (bit i <-> bin lane + 32 i), maximum peak logit
     float mx = -INFINITY;
     uint32_t mask = 0;
     for (int k = lane, i = 0; k < n_bins; k += 32, ++i) {
-      if (is_peak(x, n_bins, k, spw)) {
+      bool pk;
+      if (SPW5) {
+        const float c = x[k];
+        pk = (c > fmaxf(m4[k - 5], x[k - 1])) && (c >= fmaxf(m4[k + 1], x[k + 5]));
+      } else {
+        pk = is_peak(x, n_bins, k, spw);
+      }
+      if (pk) {
         mx = fmaxf(mx, x[k]);
         mask |= 1u << i;
       }
@@ -148,23 +173,26 @@ int emissions_run(const float* logits, const float* prior, int B, int T, int n_b
                   int out_log, float* out, cudaStream_t stream) {
   const long long n_frames = (long long)B * T;
   if (n_frames == 0) return VIT_OK;
-  const size_t smem = (size_t)kEmisWarps * n_bins * sizeof(float);
   if (n_bins > 1024) return VIT_ERR_UNSUPPORTED_ALGO;                 // 32 peak flags per lane
+  if (model != 0 && model != 1) return VIT_ERR_INVALID_ARGUMENT;
+  const bool fast = spw == 5 && n_bins >= 7;
+  const size_t smem = fast ? (size_t)kEmisWarps * 3 * (n_bins + 16) * sizeof(float) : (size_t)kEmisWarps * n_bins * sizeof(float);
   int num_sms = 148, dev = 0;
   VIT_CUDA_TRY(cudaGetDevice(&dev));
   VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   long long blocks = (n_frames + kEmisWarps - 1) / kEmisWarps;
   const long long cap = (long long)num_sms * 8;                      // grid-stride: a multiple of the SM count
   if (blocks > cap) blocks = cap;
-  if (model == 0) {
-    if (smem > 48 * 1024) VIT_CUDA_TRY(cudaFuncSetAttribute(emissions_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    emissions_kernel<0><<<(unsigned)blocks, 32 * kEmisWarps, smem, stream>>>(logits, prior, n_frames, n_bins, spw, threshold, out_log, out);
-  } else if (model == 1) {
-    if (smem > 48 * 1024) VIT_CUDA_TRY(cudaFuncSetAttribute(emissions_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    emissions_kernel<1><<<(unsigned)blocks, 32 * kEmisWarps, smem, stream>>>(logits, prior, n_frames, n_bins, spw, threshold, out_log, out);
-  } else {
-    return VIT_ERR_INVALID_ARGUMENT;
-  }
+#define VIT_EMIS_LAUNCH(M, F)                                                                                       \
+  do {                                                                                                              \
+    if (smem > 48 * 1024)                                                                                           \
+      VIT_CUDA_TRY(cudaFuncSetAttribute(emissions_kernel<M, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    emissions_kernel<M, F><<<(unsigned)blocks, 32 * kEmisWarps, smem, stream>>>(logits, prior, n_frames, n_bins, spw, \
+                                                                                threshold, out_log, out);          \
+  } while (0)
+  if (model == 0) { if (fast) VIT_EMIS_LAUNCH(0, true); else VIT_EMIS_LAUNCH(0, false); }
+  else { if (fast) VIT_EMIS_LAUNCH(1, true); else VIT_EMIS_LAUNCH(1, false); }
+#undef VIT_EMIS_LAUNCH
   note_launch();
   VIT_CUDA_TRY(cudaGetLastError());
   return VIT_OK;
