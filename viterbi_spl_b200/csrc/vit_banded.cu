@@ -18,7 +18,8 @@
 // imm matrix, imm/transition_matrix.py:4-31) simply takes the dense tensor-memory kernel.
 //
 // Kernel: no clusters, no exchange -- one CTA per SM owns 8 clips for all T steps.  4 independent pipelines of 3 warps
-// (2 clips each, named barriers).  A thread owns 4 consecutive targets and keeps their 4 x (2d+1) band entries in
+// (2 clips each, named barriers; measured faster than 2 pipelines x 4 clips: the step is a dependency chain, and more
+// pipelines hide more of it).  A thread owns 4 consecutive targets and keeps their 4 x (2d+1) band entries in
 // REGISTERS for the whole kernel; its window of delta_{t-1} (4 + 2d values per clip) is 8-9 aligned LDS.128 at
 // compile-time offsets, its 4 results one STS.128.  The dense target row
 // (unvoiced) is split over the 3 warps of a pipeline; its value and max_i delta_i travel as per-warp partials in shared
@@ -111,18 +112,23 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
     int len[bCPT];
 #pragma unroll
     for (int c = 0; c < bCPT; ++c) len[c] = s_len[c0 + c];
-    const int maxlen = max(len[0], len[1]);
+    int maxlen = 0;
+#pragma unroll
+    for (int c = 0; c < bCPT; ++c) maxlen = max(maxlen, len[c]);
     // address of logE[clip][t][j0], advanced one frame per step; the history sits at a fixed distance
     const float* pe[bCPT];
 #pragma unroll
     for (int c = 0; c < bCPT; ++c) pe[c] = log_emis + (size_t)(seq0 + c0 + c) * T_max * S + j0;
     const int jd_off = jd - j0;                              // logE[..][jd] relative to pe[c]
 
-    float ed_prev[bCPT] = {0.f, 0.f};                        // logE[t-1][jd] of my clips
+    float ed_prev[bCPT];                                     // logE[t-1][jd] of my clips
+#pragma unroll
+    for (int c = 0; c < bCPT; ++c) ed_prev[c] = 0.f;
     for (int t = 0; t < maxlen; ++t) {
       const int buf = t & 1;
       // keep the two running pointers in registers (ptxas would otherwise re-derive the 64-bit address of every load)
-      asm volatile("" : "+l"(pe[0]), "+l"(pe[1]));
+#pragma unroll
+      for (int c = 0; c < bCPT; ++c) asm volatile("" : "+l"(pe[c]));
       bool live[bCPT];
 #pragma unroll
       for (int c = 0; c < bCPT; ++c) live[c] = t < len[c];
