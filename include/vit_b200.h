@@ -88,6 +88,11 @@ typedef struct vit_decode_opts {
   int32_t skip_backtrace;
   int32_t reserved2;
   const vit_structure* structure; /* HOST pointer or NULL: what vit_analyze_structure_f32 found for d_logA_T */
+  /* Optional second cudaStream_t for the backtrace (history-based algorithms): it is ordered after the forward kernel
+   * by an event, so the caller's NEXT decode on `stream` overlaps it.  The caller must then (a) wait on this stream
+   * before reading d_paths / d_scores and (b) not reuse d_workspace until the backtrace has finished -- i.e. alternate
+   * two workspaces (viterbi_spl_b200.decoder.PipelinedDecoder does).  NULL: backtrace on `stream`. */
+  void* backtrace_stream;
 } vit_decode_opts;
 
 /* Library version (VIT_B200_VERSION of the built library). */

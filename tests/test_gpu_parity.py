@@ -313,6 +313,25 @@ def test_frame_slabs_resume_from_the_delta_history(Decoder, S, T, B, slab):
     assert np.array_equal(paths.cpu().numpy(), want_p) and np.array_equal(scores.cpu().numpy(), want_s)
 
 
+@pytest.mark.parametrize('algo', ['tmem', 'banded', 'cluster'])
+def test_pipelined_decoder_overlaps_backtrace_without_changing_results(Decoder, algo):
+    from viterbi_spl_b200 import PipelinedDecoder
+    A, pi = hmm_params.synthetic_hmm('dcnet')
+    logA_T, log_pi = hmm_params.log_params(A, pi)
+    S, T, B = 321, 400, 30
+    batches = [synth.batch('dense_softmax', B, T, S, seed0=100 * k) for k in range(5)]
+    dec = Decoder(logA_T, log_pi, algo=algo)
+    pd = PipelinedDecoder(dec)
+    outs = []
+    for E in batches:
+        outs.append(pd.submit(torch.as_tensor(E).cuda()))
+    pd.finish()
+    torch.cuda.synchronize()
+    for E, (p, s) in zip(batches, outs):
+        want_p, want_s = c_oracle.decode_batch_c(logA_T, log_pi, E)
+        assert np.array_equal(p.cpu().numpy(), want_p) and np.array_equal(s.cpu().numpy(), want_s)
+
+
 def test_device_api_lengths_and_untouched_inputs(Decoder):
     S, T, B = 97, 33, 6
     A, pi = synth.dyadic_hmm(S, seed=9)

@@ -10,7 +10,7 @@ All compute runs in ``libvit_b200.so`` (hand-written CUDA behind the C ABI in in
 fallback -- constructing a decoder without the library or without a GPU raises.
 """
 from . import _lib, hmm_params, synth  # noqa: F401
-from .decoder import ViterbiDecoder, decode_batch  # noqa: F401
+from .decoder import PipelinedDecoder, ViterbiDecoder, decode_batch  # noqa: F401
 from .posterior import ForwardBackward  # noqa: F401
 
 __version__ = '0.1.0'

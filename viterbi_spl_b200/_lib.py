@@ -33,7 +33,7 @@ class DecodeOpts(ctypes.Structure):
                 ('ev_forward_begin', ctypes.c_void_p), ('ev_forward_end', ctypes.c_void_p),
                 ('frame_begin', ctypes.c_int32), ('frame_end', ctypes.c_int32),
                 ('skip_backtrace', ctypes.c_int32), ('reserved2', ctypes.c_int32),
-                ('structure', ctypes.POINTER(Structure))]
+                ('structure', ctypes.POINTER(Structure)), ('backtrace_stream', ctypes.c_void_p)]
 
 
 class VitError(RuntimeError):

@@ -10,6 +10,13 @@ namespace vit {
 static std::atomic<uint64_t> g_launches{0};
 static thread_local std::string t_last_cuda_error;
 
+static thread_local cudaStream_t t_backtrace_stream = nullptr;
+cudaStream_t backtrace_stream_override() { return t_backtrace_stream; }
+struct BacktraceStreamScope {
+  explicit BacktraceStreamScope(cudaStream_t s) { t_backtrace_stream = s; }
+  ~BacktraceStreamScope() { t_backtrace_stream = nullptr; }
+};
+
 void note_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 int cuda_fail(cudaError_t e) {
@@ -145,6 +152,7 @@ int vit_decode_f32_ex(const float* d_logA_T, const float* d_log_pi, const float*
   if (algo < 0) return algo;
   if (!d_workspace) return VIT_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t st = (cudaStream_t)stream;
+  BacktraceStreamScope bt_scope(opts ? (cudaStream_t)opts->backtrace_stream : nullptr);
   cudaEvent_t ev0 = opts ? (cudaEvent_t)opts->ev_forward_begin : nullptr;
   cudaEvent_t ev1 = opts ? (cudaEvent_t)opts->ev_forward_end : nullptr;
   const int f_begin = opts ? opts->frame_begin : 0;

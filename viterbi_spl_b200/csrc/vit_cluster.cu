@@ -407,6 +407,18 @@ backtrace_fixup_kernel(const float* __restrict__ logA_T, const float* __restrict
 // shared with vit_tmem.cu: both forward kernels leave the same fp32 delta history behind
 int launch_hist_backtrace(const float* logA_T, const float* hist, const int32_t* lengths, int B, int T_max, int S,
                           int64_t* paths, float* scores, cudaStream_t stream) {
+  // vit_decode_opts.backtrace_stream: run the walk on a second stream, ordered after the forward kernel, so that the
+  // caller's next forward launch on `stream` overlaps it (the walk is latency-bound and leaves the SMs almost idle)
+  if (cudaStream_t bt = backtrace_stream_override()) {
+    if (bt != stream) {
+      cudaEvent_t ev;
+      VIT_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      VIT_CUDA_TRY(cudaEventRecord(ev, stream));
+      VIT_CUDA_TRY(cudaStreamWaitEvent(bt, ev, 0));
+      VIT_CUDA_TRY(cudaEventDestroy(ev));      // released by the runtime once the wait has been satisfied
+      stream = bt;
+    }
+  }
   const int nseg_max = (T_max + kBtSeg - 1) / kBtSeg;
   const long long warps = (long long)B * nseg_max;
   const dim3 block(kBtWarps * 32);

@@ -11,6 +11,7 @@ namespace vit {
 // ---- host-side bookkeeping (vit_api.cu owns the storage) -------------------------------------------------------
 void note_launch(int n = 1);          // bumps the process-wide kernel launch counter
 int cuda_fail(cudaError_t e);         // records the message, returns VIT_ERR_CUDA
+cudaStream_t backtrace_stream_override();   // vit_decode_opts.backtrace_stream of the call in flight on this thread, or 0
 #define VIT_CUDA_TRY(expr)                                   \
   do {                                                       \
     cudaError_t vit_e_ = (expr);                             \

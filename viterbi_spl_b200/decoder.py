@@ -54,21 +54,27 @@ class ViterbiDecoder:
         self._copy_stream = None
 
     # ---- device path ---------------------------------------------------------------------------------------
-    def _workspace(self, nbytes):
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = None
-            self._ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
-        return self._ws
+    def _workspace(self, nbytes, slot=0):
+        if self._ws is None:
+            self._ws = {}
+        ws = self._ws.get(slot)
+        if ws is None or ws.numel() < nbytes:
+            self._ws[slot] = None
+            ws = self._ws[slot] = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+        return ws
 
     def decode_device(self, log_emis, lengths=None, paths=None, scores=None, want_tables=False, stream=None,
-                      forward_events=None, frame_range=None, backtrace=True):
+                      forward_events=None, frame_range=None, backtrace=True, backtrace_stream=None, workspace_slot=0):
         """log_emis: CUDA float32 [B, T, S] contiguous; lengths: CUDA int32 [B] or None.
         Returns (paths int64 [B, T], scores float32 [B]) CUDA tensors (+ (T1 float32, T2 uint16) if want_tables).
         Asynchronous on `stream` (default: torch's current stream).  forward_events: optional pair of
         torch.cuda.Event(enable_timing=True) recorded by the library around the forward kernel.
         frame_range=(t0, t1) runs the recursion over those frames only, resuming (t0 > 0) from the delta history the
         previous call left in this decoder's workspace; backtrace=False skips the backtrace (all but the last range).
-        Frame ranges need the tmem algorithm."""
+        Frame ranges need the tmem algorithm.
+        backtrace_stream: run the backtrace on that stream (ordered after the forward kernel) so that the next decode
+        on `stream` overlaps it; the caller then owns the synchronisation (see PipelinedDecoder) and must give
+        consecutive calls different `workspace_slot`s."""
         assert log_emis.is_cuda and log_emis.dtype == torch.float32 and log_emis.is_contiguous()
         B, T, S = log_emis.shape
         assert S == self.S, f'emissions have {S} states, model has {self.S}'
@@ -82,7 +88,7 @@ class ViterbiDecoder:
                 if scores is None:
                     scores = torch.empty((B,), dtype=torch.float32, device=self.device)
                 algo = _lib.ALGO_BACKPOINTER if want_tables else self.algo
-                ws = self._workspace(_lib.workspace_bytes(B, T, S, algo))      # (banded needs no more than auto's choice)
+                ws = self._workspace(_lib.workspace_bytes(B, T, S, algo), workspace_slot)   # (banded needs no more than auto's choice)
                 opts = _lib.DecodeOpts(algo=algo)
                 T1 = T2 = None
                 if want_tables:
@@ -100,6 +106,8 @@ class ViterbiDecoder:
                     opts.frame_begin, opts.frame_end = int(frame_range[0]), int(frame_range[1])
                     assert 0 <= opts.frame_begin < opts.frame_end <= T, 'frame_range must be a non-empty range in [0, T]'
                 opts.skip_backtrace = 0 if backtrace else 1
+                if backtrace_stream is not None:
+                    opts.backtrace_stream = backtrace_stream.cuda_stream
                 if algo in (_lib.ALGO_AUTO, _lib.ALGO_BANDED):
                     opts.structure = ctypes.pointer(self.structure)
                 rc = self.lib.vit_decode_f32_ex(_ptr(self.logA_T), _ptr(self.log_pi), _ptr(log_emis), _ptr(lengths),
@@ -189,6 +197,44 @@ class ViterbiDecoder:
         if torch.is_tensor(log_emis) and log_emis.is_cuda:
             return self.decode_device(log_emis, lengths)
         return self.decode_host(log_emis, lengths)
+
+
+class PipelinedDecoder:
+    """Back-to-back batches with the (latency-bound) backtrace of batch k overlapping the forward recursion of batch
+    k+1: the forward kernels run on torch's current stream, the backtraces on a second stream, and two workspaces
+    alternate so that a history is never overwritten while it is still being walked.
+
+        pd = PipelinedDecoder(decoder)
+        for emis in batches:                       # CUDA tensors [B, T, S]
+            paths, scores = pd.submit(emis)        # asynchronous; results valid after pd.finish() (or pd.wait(k))
+        pd.finish()
+    """
+
+    def __init__(self, decoder):
+        self.dec = decoder
+        self.bt_stream = torch.cuda.Stream(device=decoder.device)
+        self._done = [None, None]                  # event: backtrace that last used workspace slot i has finished
+        self._k = 0
+
+    def submit(self, log_emis, lengths=None, paths=None, scores=None, forward_events=None):
+        slot = self._k & 1
+        main = torch.cuda.current_stream()
+        if self._done[slot] is not None:
+            main.wait_event(self._done[slot])      # the forward about to run overwrites that slot's history
+        out = self.dec.decode_device(log_emis, lengths, paths, scores, forward_events=forward_events,
+                                     backtrace_stream=self.bt_stream, workspace_slot=slot)
+        ev = torch.cuda.Event()
+        ev.record(self.bt_stream)
+        self._done[slot] = ev
+        self._k += 1
+        return out
+
+    def finish(self):
+        """Make torch's current stream wait for every outstanding backtrace (results are then ordered as usual)."""
+        main = torch.cuda.current_stream()
+        for ev in self._done:
+            if ev is not None:
+                main.wait_event(ev)
 
 
 def decode_batch(log_emis, logA_T, log_pi, lengths=None, algo='auto'):
