@@ -159,7 +159,7 @@ def test_reference_entry_points(Decoder):
 SHAPES = [(1, 1, 1), (2, 3, 1), (7, 5, 3), (31, 40, 2), (32, 9, 33), (33, 17, 5), (64, 21, 15), (96, 30, 4), (97, 50, 5),
           (128, 12, 3), (160, 14, 8), (192, 20, 6), (193, 25, 6), (200, 64, 9), (321, 100, 33), (361, 120, 70), (364, 30, 5),
           (365, 20, 3), (384, 18, 16), (385, 16, 9), (500, 15, 4), (722, 24, 17), (769, 9, 15),
-          (97, 1000, 6), (361, 700, 5), (40, 2049, 3)]     # long clips: many backtrace segments (speculate + fix up)
+          (97, 1000, 6), (361, 700, 5), (40, 2049, 3), (722, 600, 20)]     # long clips: many backtrace segments (speculate + fix up)
 
 
 @pytest.mark.parametrize('S,T,B', SHAPES)
