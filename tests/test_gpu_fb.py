@@ -15,11 +15,16 @@ GAMMA_ATOL = 1e-4
 LOGLIK_RTOL = 1e-5
 
 
-@pytest.fixture(scope='module')
-def FB(cuda_lib):
+@pytest.fixture(scope='module', params=['tc', 'simt'])
+def FB(cuda_lib, request):
+    """Both kernels behind vit_forward_backward_f32: the tcgen05 tensor-core one (default where the shape fits) and the
+    FFMA one (VIT_FB_IMPL=simt; also the fallback for S = 722)."""
+    import os
     assert torch.cuda.is_available()
     from viterbi_spl_b200 import ForwardBackward
-    return ForwardBackward
+    os.environ['VIT_FB_IMPL'] = request.param
+    yield ForwardBackward
+    os.environ.pop('VIT_FB_IMPL', None)
 
 
 def random_hmm(S, rng, sparse=False):

@@ -1,5 +1,6 @@
 // extern "C" surface of libvit_b200.so (declared in include/vit_b200.h).
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -64,6 +65,19 @@ int banded_decode(const float* logA_T, const float* log_pi, const float* log_emi
                   int T_max, int S, const vit_structure* st, void* workspace, size_t workspace_bytes, int64_t* paths,
                   float* scores, float* delta_out, cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t stream);
 int analyze_structure(const float* A, int S, vit_structure* out);
+
+// vit_fb_tc.cu
+bool fb_tc_supported(int S);
+size_t fb_tc_workspace_bytes(int B, int T_max, int S);
+int fb_tc_run(const float* A, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S,
+              void* workspace, size_t workspace_bytes, float* gamma, float* loglik, cudaStream_t stream);
+// Which of the two forward-backward kernels runs: VIT_FB_IMPL=tc selects the tcgen05 tensor-core kernel where the shape
+// fits, VIT_FB_IMPL=simt (and the default, see DESIGN.md section 3.8 for the measurements behind it) the FFMA kernel.
+static bool fb_use_tc(int S) {
+  const char* e = getenv("VIT_FB_IMPL");
+  if (e && !strcmp(e, "tc")) return fb_tc_supported(S);
+  return false;
+}
 
 static int check_shape(int B, int T_max, int S) {
   if (B < 0 || T_max < 1 || S < 1) return VIT_ERR_INVALID_ARGUMENT;
@@ -185,8 +199,10 @@ int vit_fb_workspace_bytes(int B, int T_max, int S, size_t* out_bytes) {
   if (!out_bytes) return VIT_ERR_INVALID_ARGUMENT;
   int rc = check_shape(B, T_max, S);
   if (rc != VIT_OK) return rc;
-  if (!fb_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;
-  *out_bytes = fb_workspace_bytes(B, T_max, S);
+  if (!fb_supported(S) && !fb_tc_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;
+  const size_t a = fb_supported(S) ? fb_workspace_bytes(B, T_max, S) : 0;
+  const size_t b = fb_tc_supported(S) ? fb_tc_workspace_bytes(B, T_max, S) : 0;
+  *out_bytes = a > b ? a : b;
   return VIT_OK;
 }
 
@@ -196,9 +212,13 @@ int vit_forward_backward_f32(const float* d_A, const float* d_pi, const float* d
   int rc = check_shape(B, T_max, S);
   if (rc != VIT_OK) return rc;
   if (!d_A || !d_pi || !d_gamma || (!d_lik && B > 0)) return VIT_ERR_INVALID_ARGUMENT;
-  if (!fb_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;
+  if (!fb_supported(S) && !fb_tc_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;
   if (!d_workspace) return VIT_ERR_WORKSPACE_TOO_SMALL;
   if (((uintptr_t)d_workspace & 255u) != 0) return VIT_ERR_MISALIGNED;
+  if (fb_use_tc(S))
+    return fb_tc_run(d_A, d_pi, d_lik, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_gamma, d_loglik,
+                     (cudaStream_t)stream);
+  if (!fb_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;
   return fb_run(d_A, d_pi, d_lik, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_gamma, d_loglik, nullptr,
                 nullptr, (cudaStream_t)stream);
 }

@@ -96,6 +96,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// CTA-scope acquire (the default semantics): what bulk-async / tcgen05.commit completions need.  The .cluster-scope form
+// above makes ptxas append CCTL.IVALL (a whole-L1 invalidate) to every successful wait.
+__device__ __forceinline__ bool mbar_try_wait_cta(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait_cta(bar, parity)) {}
+}
 // make this thread's generic-proxy shared-memory writes visible to the async proxy (bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -327,7 +327,7 @@ fb_pass_kernel(const float* __restrict__ packedT, const float* __restrict__ pack
   if (C > 1) cluster_sync();
 }
 
-// log L = sum_t log c_t : one warp per clip, double accumulation
+// log L = sum_t log c_t : one warp per clip, double accumulation (shared with vit_fb_tc.cu)
 __global__ void fb_loglik_kernel(const float* __restrict__ cnorm, const int32_t* __restrict__ lengths, int B, int T_max,
                                  float* __restrict__ loglik) {
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;

@@ -1,0 +1,452 @@
+// Forward-backward on the 5th-generation tensor cores (tcgen05.mma, accumulators and the A operand in tensor memory).
+//
+// Same recursion and the same deferred-normaliser scheme as vit_fb.cu (oracle/fb_oracle.py states the semantics; there
+// is no reference implementation: parity unpinned).  Per step the matrix-vector products of all clips of a cluster are
+// ONE small GEMM  D[128 x 32] = M_shard[128 x K] . V[K x 32]:
+//   * M_shard  = this CTA's <= 127 rows of A^T (forward) / A (backward), all K source positions, resident in TENSOR
+//                MEMORY for the whole kernel as the A operand of the "TS" form of tcgen05.mma.  fp32 does not fit and
+//                TF32's 10-bit mantissa cannot hold 1e-4 on gamma, so every fp32 value x is split into two bf16 terms
+//                x = hi + lo (16 mantissa bits); four MMAs per K block -- hi.hi, hi.lo, lo.hi, lo.lo -- accumulate in fp32.
+//                Row 127 of the forward operand is all ones: D[127][n] = sum_k alpha~[k][n] is the normaliser c_{t-1}
+//                for free.
+//   * V        = alpha~_{t-1} (forward) / w_{t+1} (backward) of 32 clips, bf16 hi and lo copies in shared memory in the
+//                canonical no-swizzle MN-major layout (8 x 16-byte core matrices; validated by tools/microbench_umma.cu),
+//                double buffered.  Each CTA writes the rows of its own states and pushes them to its peers with bulk
+//                async DSMEM copies that complete on the receiver's mbarrier.
+//   * D        = fp32 in TMEM; the 128 threads (thread m = row m = one state) read their row with tcgen05.ld, scale
+//                by 1/c, multiply by the emission likelihoods, store alpha~ / gamma, and write the next V.
+// One thread issues the 96 UTCHMMA of a step and commits them to an mbarrier; the step is a dependency chain
+// (wait V -> MMA -> epilogue -> exchange), so the tensor pipe is lightly used -- the point is the ~4x shorter chain than
+// the FFMA kernel's, not tensor throughput.
+#include <cstdlib>
+#include <cuda_bf16.h>
+
+#include "vit_common.cuh"
+
+namespace vit {
+
+constexpr int cN = 32;            // clips per cluster (N of the MMA)
+constexpr int cM = 128;           // rows of the MMA = TMEM lanes = threads
+constexpr int cThreads = 128;
+constexpr int cTmemCols = 512;
+
+struct TcPlan {
+  int C;        // CTAs per cluster
+  int NCP;      // K positions per shard (multiple of 16); shard r owns K positions [r*NCP, r*NCP + nc(r))
+  int KP;       // C * NCP
+  int base, rem;
+};
+
+static bool make_tc_plan(int S, TcPlan* p) {
+  if (S < 1) return false;
+  const int C = (S + 126) / 127;                          // <= 127 states per CTA: row 127 is the ones row
+  if (C > 8) return false;
+  p->C = C;
+  p->base = S / C;
+  p->rem = S % C;
+  const int ncmax = p->base + (p->rem ? 1 : 0);
+  p->NCP = (ncmax + 15) / 16 * 16;
+  p->KP = C * p->NCP;
+  if (p->KP + cN > cTmemCols) return false;               // A hi + lo = KP columns, D = 32 columns
+  const size_t smem = (size_t)2 * 2 * p->KP * cN * 2 + 256;
+  return smem <= 200 * 1024;
+}
+
+static size_t tc_smem_bytes(const TcPlan& p) { return (size_t)2 * 2 * p.KP * cN * 2 + 256; }
+static size_t tc_packed_words(const TcPlan& p) { return (size_t)p.C * 2 * cM * (p.KP / 2); }
+
+// packed [C][term: hi, lo][128 rows][KP/2 columns] uint32: column c = bf16(k = 2c) | bf16(k = 2c + 1) << 16.
+// transposed = false: row m of shard r is M[j][.] = A stored [j][i] ... the operand is "rows = outputs, K = inputs":
+//   forward : out j, in i, value A[i][j]  -> transposed read of the source-major A
+//   backward: out i, in j, value A[i][j]  -> direct read
+__global__ void tc_pack_kernel(const float* __restrict__ A, int S, TcPlan p, bool transposed, bool ones_row,
+                               uint32_t* __restrict__ packed) {
+  const int cols = p.KP / 2;
+  const size_t total = (size_t)p.C * cM * cols;
+  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(x % cols);
+    const int m = (int)((x / cols) % cM);
+    const int r = (int)(x / ((size_t)cols * cM));
+    const int nc = p.base + (r < p.rem ? 1 : 0);
+    uint32_t hi = 0, lo = 0;
+    for (int h = 0; h < 2; ++h) {
+      const int kp = 2 * c + h;
+      const int ci = kp / p.NCP, l = kp - ci * p.NCP;
+      const int nci = p.base + (ci < p.rem ? 1 : 0);
+      float v = 0.f;
+      if (l < nci) {
+        const int in = ci * p.base + min(ci, p.rem) + l;
+        if (m < nc) {
+          const int out = r * p.base + min(r, p.rem) + m;
+          v = transposed ? A[(size_t)in * S + out] : A[(size_t)out * S + in];
+        } else if (m == cM - 1 && ones_row) {
+          v = 1.f;
+        }
+      }
+      const __nv_bfloat16 bh = __float2bfloat16(v);
+      const __nv_bfloat16 bl = __float2bfloat16(v - __bfloat162float(bh));
+      hi |= (uint32_t)__bfloat16_as_ushort(bh) << (16 * h);
+      lo |= (uint32_t)__bfloat16_as_ushort(bl) << (16 * h);
+    }
+    packed[((size_t)(r * 2 + 0) * cM + m) * cols + c] = hi;
+    packed[((size_t)(r * 2 + 1) * cM + m) * cols + c] = lo;
+  }
+}
+
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* d) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(d);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+                 "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+                 "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+                 "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 8 fp32 -> 8 bf16 hi (16 bytes) and 8 bf16 lo
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16(v[2 * i]), h1 = __float2bfloat16(v[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16(v[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16(v[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(cThreads, 1)
+fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__ pi, const float* __restrict__ lik,
+                  const int32_t* __restrict__ lengths, int B, int T_max, int S, TcPlan p, float* __restrict__ gamma,
+                  float* __restrict__ cnorm, int dev) {
+  // dev: timing experiments only (results invalid): 1 = no HBM traffic, 2 = no exchange, 4 = no MMAs
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int KP = p.KP, NCP = p.NCP;
+  const uint32_t LBO = (cN / 8) * 128;                  // bytes between groups of 8 K positions
+  const uint32_t term_bytes = (uint32_t)KP * cN * 2;    // one bf16 copy of V
+  const uint32_t buf_bytes = 2 * term_bytes;            // hi + lo
+  uint8_t* sV = smem_raw;                               // [2 buffers][2 terms][KP/8][4 cores][8 k][8 n] bf16
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * buf_bytes);     // [0..1] V ready, [2] MMA done
+  __shared__ float s_c[2][cN];                          // 1 / normalisers of the step (forward: from D row 127)
+  __shared__ float s_craw[cN];
+  __shared__ int s_len[cN];
+  __shared__ uint32_t s_tmem_base;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t C = cluster_nctarank();
+  const uint32_t rank = cluster_ctarank();
+  const int nc_mine = p.base + ((int)rank < p.rem ? 1 : 0);
+  const int j = (int)rank * p.base + min((int)rank, p.rem) + tid;      // my state (row tid)
+  const bool row_ok = tid < nc_mine;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&s_tmem_base)), "n"(cTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int x = tid; x < (int)(2 * buf_bytes / 16); x += cThreads) reinterpret_cast<uint4*>(sV)[x] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_bar[0]), 1);
+    mbar_init(smem_u32(&s_bar[1]), 1);
+    mbar_init(smem_u32(&s_bar[2]), 1);
+    mbar_fence_init();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = s_tmem_base;
+  const uint32_t tlane = tbase + ((uint32_t)(warp * 32) << 16);
+  {
+    // A operand -> TMEM: hi copy in columns [0, KP/2), lo copy in [KP/2, KP); row = lane
+    const int cols = KP / 2;
+#pragma unroll 1
+    for (int term = 0; term < 2; ++term) {
+      const uint4* src = reinterpret_cast<const uint4*>(packed + ((size_t)(rank * 2 + term) * cM + tid) * cols);
+      for (int x = 0; x < cols / 4; ++x) {
+        const uint4 v = src[x];
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                     ::"r"(tlane + term * cols + 4 * x), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the zero-filled V buffers, for the tensor core
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (C > 1) cluster_sync();
+
+  const uint32_t d_tmem = tbase + KP;                    // accumulator columns [KP, KP + 32)
+  // instruction descriptor: D = F32, A = B = BF16, A K-major (TMEM), B MN-major, N >> 3, M >> 4
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(cN >> 3) << 17) | ((uint32_t)(cM >> 4) << 24);
+  const uint32_t slice_bytes = (uint32_t)NCP * cN * 2;   // my rows of one bf16 copy: contiguous in the canonical layout
+  const uint32_t tx_bytes = (C - 1) * 2 * slice_bytes;
+  const long long gamma_delta = reinterpret_cast<const char*>(gamma) - reinterpret_cast<const char*>(lik);
+
+  uint32_t g = 0;           // the MMA of iteration g reads V buffer g & 1; the epilogue writes buffer (g + 1) & 1
+  uint32_t ph[2] = {0, 0};  // completed phases of the two "V rows have landed" barriers
+  uint32_t n_mma = 0;       // MMA batches committed so far (parity of s_bar[2])
+  for (int seq0 = (int)cluster_id_x() * cN; seq0 < B; seq0 += (int)num_clusters_x() * cN) {
+    __syncthreads();
+    // no CTA may start pushing rows of the next sub-batch while a peer's last MMA still reads that buffer
+    if (C > 1) cluster_sync();
+    if (tid < cN) {
+      const int b = seq0 + tid;
+      s_len[tid] = b < B ? (lengths ? lengths[b] : T_max) : 0;
+    }
+    __syncthreads();
+    int maxlen = 0;
+    for (int n = 0; n < cN; ++n) maxlen = max(maxlen, s_len[n]);
+    const int n_iter = BWD ? maxlen : maxlen + 1;         // forward: one extra MMA-only step yields the last normaliser
+
+    bool first = true;
+    for (int it = 0; it < n_iter; ++it, ++g) {
+      const int t = BWD ? maxlen - 1 - it : it;
+      const uint32_t cur = g & 1u, nxt = cur ^ 1u;
+      const bool tail = !BWD && it == maxlen;             // forward's extra step
+      // this step's likelihoods (backwards also the stored alpha~): issued first, used after the MMAs
+      float e[cN], al[cN];
+      // lik[clip n][t][j] = p_t + n * (T_max * S): one running 64-bit pointer instead of 32 address computations
+      const size_t clip_stride = (size_t)T_max * S;
+      const float* p_t = lik + ((size_t)seq0 * T_max + (tail ? 0 : t)) * S + j;
+      {
+        const float* pn = p_t;
+#pragma unroll
+        for (int n = 0; n < cN; ++n, pn += clip_stride) {
+          const bool lv = row_ok && !tail && t < s_len[n] && !(dev & 1);
+          e[n] = lv ? ld_global_nc_f32(pn) : 0.f;
+          if (BWD) al[n] = lv ? ld_global_nc_f32(reinterpret_cast<const float*>(reinterpret_cast<const char*>(pn) + gamma_delta)) : 0.f;
+        }
+      }
+      float d[cN];
+      if (!first) {
+        if (C > 1 && !(dev & 2)) { mbar_wait_cta(smem_u32(&s_bar[cur]), ph[cur] & 1u); ++ph[cur]; }   // peers' rows of V have landed
+        if (tid == 0 && !(dev & 4)) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t vb = smem_u32(sV) + cur * buf_bytes;
+          // descriptor = start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46; a K block of 16 advances the
+          // start field by 2 LBO >> 4 (the smem window is < 256 KB, so the 14-bit field never carries)
+          const uint32_t desc_hi32 = (128u >> 4) | (1u << 14);
+          uint32_t lo_hi = ((vb >> 4) & 0x3FFF) | (((LBO >> 4) & 0x3FFF) << 16);
+          uint32_t lo_lo = (((vb + term_bytes) >> 4) & 0x3FFF) | (((LBO >> 4) & 0x3FFF) << 16);
+          uint32_t a_hi = tbase, a_lo = tbase + KP / 2;
+          const int nkb = KP / 16;
+          uint32_t acc = 0;
+#pragma unroll 4
+          for (int kb = 0; kb < nkb; ++kb) {
+            const uint64_t desc_hi = ((uint64_t)desc_hi32 << 32) | lo_hi;
+            const uint64_t desc_lo = ((uint64_t)desc_hi32 << 32) | lo_lo;
+            tc_mma(d_tmem, a_hi, desc_hi, idesc, acc);
+            acc = 1;
+            tc_mma(d_tmem, a_hi, desc_lo, idesc, 1);
+            tc_mma(d_tmem, a_lo, desc_hi, idesc, 1);
+            tc_mma(d_tmem, a_lo, desc_lo, idesc, 1);     // without lo.lo the gamma error reaches 1.03e-4 (measured)
+            lo_hi += (2 * LBO) >> 4;
+            lo_lo += (2 * LBO) >> 4;
+            a_hi += 8;
+            a_lo += 8;
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar[2])) : "memory");
+        }
+        if (BWD && tid < 2 * cN) {
+          // 1 / c_t (threads 0-31) and 1 / c_{t+1} (32-63) of the 32 clips: fetched while the MMAs run
+          const int n = tid & (cN - 1), tt = t + (tid >> 5);
+          s_c[tid >> 5][n] = (tt < s_len[n]) ? 1.f / cnorm[(size_t)(seq0 + n) * T_max + tt] : 1.f;
+        }
+        if (!(dev & 4)) { mbar_wait_cta(smem_u32(&s_bar[2]), n_mma & 1u); ++n_mma; }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tc_ld32(tlane + KP, d);
+        if (!BWD && warp == 3) {
+          // row 127 = the ones row: c_{t-1}[n].  Lane 31 holds the 32 sums; the warp turns them into 1 / c and one CTA per
+          // cluster records them
+          if (tid == cM - 1) {
+#pragma unroll
+            for (int n = 0; n < cN; ++n) s_craw[n] = d[n];
+          }
+          __syncwarp();
+          const int n = tid & 31;
+          const float c = s_craw[n];
+          s_c[0][n] = c > 0.f ? 1.f / c : 0.f;                        // every thread multiplies by 1 / c
+          if (rank == 0 && t - 1 < s_len[n] && !(dev & 1)) cnorm[(size_t)(seq0 + n) * T_max + (t - 1)] = c;
+        }
+      }
+      if (BWD && first && tid < cN) s_c[0][tid] = (t < s_len[tid]) ? 1.f / cnorm[(size_t)(seq0 + tid) * T_max + t] : 1.f;
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();                                    // s_c visible; D fully read before the next MMA batch
+      if (tail) { first = false; continue; }
+
+      float v[cN];
+      {
+        float* gn = reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<float*>(p_t)) + gamma_delta);
+#pragma unroll
+        for (int n = 0; n < cN; ++n, gn += clip_stride) {
+          if (!BWD) {
+            // alpha~_t = (M alpha~_{t-1} / c_{t-1}) * b_t ;  alpha~_0 = pi * b_0
+            float u;
+            if (first) u = row_ok ? pi[j] : 0.f;
+            else u = d[n] * s_c[0][n];
+            v[n] = u * e[n];
+            if (row_ok && t < s_len[n] && !(dev & 1)) st_global_cs_f32(gn, v[n]);
+          } else {
+            // beta_t = M w_{t+1} / c_{t+1} (1 at the clip's last frame); gamma_t = alpha~_t / c_t * beta_t; w_t = b_t beta_t
+            const int len = s_len[n];
+            const float be = (t == len - 1) ? 1.f : (first ? 0.f : d[n] * s_c[1][n]);
+            const bool lv = row_ok && t < len;
+            v[n] = lv ? e[n] * be : 0.f;
+            if (lv && !(dev & 1)) st_global_cs_f32(gn, al[n] * s_c[0][n] * be);
+          }
+        }
+      }
+      // my row of the next V (K position rank*NCP + tid), bf16 hi and lo: 4 core-matrix rows of 16 bytes each
+      if (row_ok) {
+        const uint32_t k = rank * NCP + tid;
+        uint8_t* row = sV + nxt * buf_bytes + (k >> 3) * LBO + (k & 7) * 16;
+#pragma unroll
+        for (int c8 = 0; c8 < cN / 8; ++c8) {
+          uint4 hi, lo;
+          split8(v + 8 * c8, hi, lo);
+          *reinterpret_cast<uint4*>(row + c8 * 128) = hi;
+          *reinterpret_cast<uint4*>(row + term_bytes + c8 * 128) = lo;
+        }
+      }
+      first = false;
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (C > 1 && !(dev & 2)) {
+        if (tid == 0) mbar_arrive_expect_tx(smem_u32(&s_bar[nxt]), tx_bytes);
+        if (tid < (int)(C - 1) * 2) {
+          const uint32_t peer = (rank + 1 + tid / 2) % C;
+          const uint32_t src = smem_u32(sV + nxt * buf_bytes + (tid & 1) * term_bytes + (size_t)rank * slice_bytes);
+          dsmem_bulk_copy(mapa(src, peer), src, slice_bytes, mapa(smem_u32(&s_bar[nxt]), peer));
+        }
+      }
+    }
+    // backward: the rows pushed in the last step are never consumed -- wait for them so that every armed phase is
+    // matched by exactly one wait (forward: the extra step consumed the last push)
+    if (BWD && C > 1 && !first && !(dev & 2)) { mbar_wait_cta(smem_u32(&s_bar[g & 1u]), ph[g & 1u] & 1u); ++ph[g & 1u]; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem_base), "n"(cTmemCols) : "memory");
+  if (C > 1) cluster_sync();
+}
+
+// The 16-bit-mantissa products leave a relative error of ~1e-5 per step in the SCALE of beta (forward and backward
+// normalisers no longer cancel exactly), which random-walks to ~5e-4 over 3000 frames -- but it is common to all states
+// of a frame, so renormalising every gamma_t to sum 1 removes it.  One warp per frame, HBM-bound (read + write gamma).
+__global__ void __launch_bounds__(256) fb_normalize_gamma_kernel(float* __restrict__ gamma, const int32_t* __restrict__ lengths,
+                                                                 int B, int T_max, int S) {
+  const int lane = threadIdx.x & 31;
+  const long long n_frames = (long long)B * T_max;
+  for (long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; f < n_frames;
+       f += ((long long)gridDim.x * blockDim.x) >> 5) {
+    if (lengths && (int)(f % T_max) >= lengths[f / T_max]) continue;
+    float* g = gamma + f * S;
+    float sum = 0.f;
+    for (int k = lane; k < S; k += 32) sum += g[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    for (int k = lane; k < S; k += 32) g[k] *= inv;
+  }
+}
+
+bool fb_tc_supported(int S) {
+  TcPlan p;
+  return make_tc_plan(S, &p);
+}
+
+size_t fb_tc_workspace_bytes(int B, int T_max, int S) {
+  TcPlan p;
+  if (!make_tc_plan(S, &p)) return 0;
+  size_t bytes = 2 * align_up(tc_packed_words(p) * sizeof(uint32_t), 256);
+  bytes += align_up((size_t)(B > 0 ? B : 1) * T_max * sizeof(float), 256);
+  return bytes;
+}
+
+// vit_fb.cu
+__global__ void fb_loglik_kernel(const float* __restrict__ cnorm, const int32_t* __restrict__ lengths, int B, int T_max,
+                                 float* __restrict__ loglik);
+
+int fb_tc_run(const float* A, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S,
+              void* workspace, size_t workspace_bytes, float* gamma, float* loglik, cudaStream_t stream) {
+  TcPlan p;
+  if (!make_tc_plan(S, &p)) return VIT_ERR_UNSUPPORTED_ALGO;
+  if (workspace_bytes < fb_tc_workspace_bytes(B, T_max, S)) return VIT_ERR_WORKSPACE_TOO_SMALL;
+  if (B == 0) return VIT_OK;
+  char* ws = (char*)workspace;
+  uint32_t* packed[2];
+  for (int k = 0; k < 2; ++k) {
+    packed[k] = (uint32_t*)ws;
+    ws += align_up(tc_packed_words(p) * sizeof(uint32_t), 256);
+  }
+  float* cnorm = (float*)ws;
+  if (lengths) VIT_CUDA_TRY(cudaMemsetAsync(gamma, 0, (size_t)B * T_max * S * sizeof(float), stream));
+  {
+    const size_t total = (size_t)p.C * cM * (p.KP / 2);
+    const int grid = (int)((total + 255) / 256);
+    tc_pack_kernel<<<grid, 256, 0, stream>>>(A, S, p, /*transposed=*/true, /*ones_row=*/true, packed[0]);
+    tc_pack_kernel<<<grid, 256, 0, stream>>>(A, S, p, /*transposed=*/false, /*ones_row=*/false, packed[1]);
+    note_launch(2);
+    VIT_CUDA_TRY(cudaGetLastError());
+  }
+  const size_t smem = tc_smem_bytes(p) < 120 * 1024 ? 120 * 1024 : tc_smem_bytes(p);   // one CTA per SM (whole TMEM)
+  auto kf = fb_tc_pass_kernel<false>;
+  auto kb = fb_tc_pass_kernel<true>;
+  VIT_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VIT_CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(cThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  cfg.gridDim = dim3(p.C);
+  VIT_CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, kf, &cfg));
+  if (max_clusters < 1) return VIT_ERR_UNSUPPORTED_ALGO;
+  int num_sms = 148, devid = 0;
+  VIT_CUDA_TRY(cudaGetDevice(&devid));
+  VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, devid));
+  if (max_clusters * p.C > num_sms) max_clusters = num_sms / p.C;
+  const int want = (B + cN - 1) / cN;
+  const int n_clusters = want < max_clusters ? want : max_clusters;
+  cfg.gridDim = dim3(n_clusters * p.C);
+  const char* dev_s = getenv("VIT_DEV_FLAGS");
+  const int dev = dev_s ? atoi(dev_s) : 0;
+  VIT_CUDA_TRY(cudaLaunchKernelEx(&cfg, kf, (const uint32_t*)packed[0], pi, lik, lengths, B, T_max, S, p, gamma, cnorm, dev));
+  note_launch();
+  VIT_CUDA_TRY(cudaLaunchKernelEx(&cfg, kb, (const uint32_t*)packed[1], pi, lik, lengths, B, T_max, S, p, gamma, cnorm, dev));
+  note_launch();
+  {
+    const long long warps = (long long)B * T_max;
+    long long blocks = (warps + 7) / 8;
+    if (blocks > (long long)num_sms * 16) blocks = (long long)num_sms * 16;
+    fb_normalize_gamma_kernel<<<(unsigned)blocks, 256, 0, stream>>>(gamma, lengths, B, T_max, S);
+    note_launch();
+    VIT_CUDA_TRY(cudaGetLastError());
+  }
+  if (loglik) {
+    fb_loglik_kernel<<<(B + 3) / 4, 128, 0, stream>>>(cnorm, lengths, B, T_max, loglik);
+    note_launch();
+    VIT_CUDA_TRY(cudaGetLastError());
+  }
+  return VIT_OK;
+}
+
+}  // namespace vit
