@@ -71,12 +71,20 @@ bool fb_tc_supported(int S);
 size_t fb_tc_workspace_bytes(int B, int T_max, int S);
 int fb_tc_run(const float* A, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S,
               void* workspace, size_t workspace_bytes, float* gamma, float* loglik, cudaStream_t stream);
-// Which of the two forward-backward kernels runs: VIT_FB_IMPL=tc selects the tcgen05 tensor-core kernel where the shape
-// fits, VIT_FB_IMPL=simt (and the default, see DESIGN.md section 3.8 for the measurements behind it) the FFMA kernel.
-static bool fb_use_tc(int S) {
+// Which of the two forward-backward kernels runs.  VIT_FB_IMPL=tc|simt forces one (where the shape allows); otherwise the
+// cheaper one by the measured step costs (B200, S = 361): the tcgen05 kernel steps 32 clips per 3-CTA cluster in ~8.4 us
+// on 45 co-resident clusters, the FFMA kernel 14 clips per 2-CTA cluster in ~7.7 us on 74 -- so the tensor-core kernel
+// wins whenever the batch needs fewer of its rounds (1024 clips: one round each, FFMA ahead by 8 %; 4096 clips: 3 vs 4
+// rounds, tensor cores ahead by 21 %).
+static bool fb_use_tc(int B, int S) {
   const char* e = getenv("VIT_FB_IMPL");
   if (e && !strcmp(e, "tc")) return fb_tc_supported(S);
-  return false;
+  if (e && !strcmp(e, "simt")) return !fb_supported(S) && fb_tc_supported(S);
+  if (!fb_tc_supported(S)) return false;
+  if (!fb_supported(S)) return true;
+  const double cost_tc = (double)((B + 45 * 32 - 1) / (45 * 32)) * 8.4;
+  const double cost_simt = (double)((B + 74 * 14 - 1) / (74 * 14)) * 7.7;
+  return cost_tc < cost_simt;
 }
 
 static int check_shape(int B, int T_max, int S) {
@@ -215,7 +223,7 @@ int vit_forward_backward_f32(const float* d_A, const float* d_pi, const float* d
   if (!fb_supported(S) && !fb_tc_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;
   if (!d_workspace) return VIT_ERR_WORKSPACE_TOO_SMALL;
   if (((uintptr_t)d_workspace & 255u) != 0) return VIT_ERR_MISALIGNED;
-  if (fb_use_tc(S))
+  if (fb_use_tc(B, S))
     return fb_tc_run(d_A, d_pi, d_lik, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_gamma, d_loglik,
                      (cudaStream_t)stream);
   if (!fb_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;

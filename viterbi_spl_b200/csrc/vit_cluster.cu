@@ -191,7 +191,7 @@ cluster_forward_kernel(const float* __restrict__ packedA, const float* __restric
         }
       } else {
         // delta_{t-1} from the peers has landed in buffer (g-1)&1 ?
-        if (C > 1 && !(dev & 2)) mbar_wait(smem_u32(&s_bar[buf ^ 1u]), ((g - 1) >> 1) & 1u);
+        if (C > 1 && !(dev & 2)) mbar_wait_cta(smem_u32(&s_bar[buf ^ 1u]), ((g - 1) >> 1) & 1u);
 #pragma unroll
         for (int i = 0; i < MB * NJ; ++i) acc[i] = -INFINITY;
         const float4* pD = reinterpret_cast<const float4*>(sD + (size_t)(buf ^ 1u) * MC * KP) + (bg * MB) * KP4 + q;
@@ -264,7 +264,7 @@ cluster_forward_kernel(const float* __restrict__ packedA, const float* __restric
     }
     // drain the last step's exchange.  Once it has completed, every peer has finished the K loop of its last step, so
     // none of them still reads the buffer that step 0 of this pipeline's next sub-batch will overwrite.
-    if (C > 1 && maxlen > 0 && !(dev & 2)) mbar_wait(smem_u32(&s_bar[(g - 1) & 1u]), ((g - 1) >> 1) & 1u);
+    if (C > 1 && maxlen > 0 && !(dev & 2)) mbar_wait_cta(smem_u32(&s_bar[(g - 1) & 1u]), ((g - 1) >> 1) & 1u);
     pipe_bar_sync(pipe);   // s_len is rewritten next
   }
   __syncthreads();

@@ -166,7 +166,7 @@ fb_pass_kernel(const float* __restrict__ packedT, const float* __restrict__ pack
 #pragma unroll
         for (int k = 0; k < 2 * NJ; ++k) acc[k] = 0.f;
       } else {
-        if (C > 1) mbar_wait(smem_u32(&s_bar[buf ^ 1u]), ((g - 1) >> 1) & 1u);
+        if (C > 1) mbar_wait_cta(smem_u32(&s_bar[buf ^ 1u]), ((g - 1) >> 1) & 1u);
         const float* prev = sD + (size_t)(buf ^ 1u) * MB * KP;
         if (!BWD) {
           // c_{t-1} = sum over the shards of the partial sums parked in the last K position of every shard's slice
@@ -306,7 +306,7 @@ fb_pass_kernel(const float* __restrict__ packedT, const float* __restrict__ pack
         tpipe_bar_sync(pipe);
       }
     }
-    if (C > 1 && !first) mbar_wait(smem_u32(&s_bar[(g - 1) & 1u]), ((g - 1) >> 1) & 1u);
+    if (C > 1 && !first) mbar_wait_cta(smem_u32(&s_bar[(g - 1) & 1u]), ((g - 1) >> 1) & 1u);
     if (!BWD && !first && rank == 0 && jg == 0) {
       // the last frame's normaliser of the clips that run to the end of this sub-batch
       const float* prev = sD + (size_t)((g - 1) & 1u) * MB * KP;

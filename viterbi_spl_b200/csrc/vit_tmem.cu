@@ -180,7 +180,7 @@ tmem_forward_kernel(const float* __restrict__ packedT, const float* __restrict__
       } else {
         // delta_{t-1} from the peers has landed in buffer (g-1)&1 ?  (the first step of a launch reads what the
         // resume code above, or nothing, put there)
-        if (C > 1 && !first && !(dev & 2)) mbar_wait(smem_u32(&s_bar[buf ^ 1u]), ((g - 1) >> 1) & 1u);
+        if (C > 1 && !first && !(dev & 2)) mbar_wait_cta(smem_u32(&s_bar[buf ^ 1u]), ((g - 1) >> 1) & 1u);
 #pragma unroll
         for (int i = 0; i < NPAD; ++i) acc[i] = -INFINITY;
         const float4* pD = reinterpret_cast<const float4*>(sD + (size_t)(buf ^ 1u) * MB * KP) + q;
@@ -275,7 +275,7 @@ tmem_forward_kernel(const float* __restrict__ packedT, const float* __restrict__
     }
     // drain the last step's exchange.  Once it has completed, every peer has finished the K loop of its last step, so
     // none of them still reads the buffer that the first step of this pipeline's next sub-batch will overwrite.
-    if (C > 1 && !first && !(dev & 2)) mbar_wait(smem_u32(&s_bar[(g - 1) & 1u]), ((g - 1) >> 1) & 1u);
+    if (C > 1 && !first && !(dev & 2)) mbar_wait_cta(smem_u32(&s_bar[(g - 1) & 1u]), ((g - 1) >> 1) & 1u);
     tpipe_bar_sync(pipe);   // s_len is rewritten next
   }
   tc_fence_before();
