@@ -1,6 +1,8 @@
 // Shared pieces of the tensor-memory kernels (vit_tmem.cu: max-plus Viterbi; vit_fb.cu: sum-product forward-backward):
 // the shard/tile plan, the re-layout of the [S][S] matrix into per-lane TMEM images, and the tcgen05 ld/st helpers.
 #pragma once
+#include <cstdlib>
+
 #include "vit_common.cuh"
 
 namespace vit {
@@ -27,28 +29,39 @@ struct TmemPlan {
 
 // min_pad: spare K positions wanted at the end of every shard's slice (the forward-backward kernel parks its partial
 // normaliser sums there)
+static bool try_tmem_plan(int S, int C, TmemPlan* p, int min_pad) {
+  const int NCmax = (S + C - 1) / C;
+  if (NCmax > 32 * tMaxNJ) return false;
+  p->C = C;
+  p->base = S / C;
+  p->rem = S % C;
+  p->NCmax = NCmax;
+  p->NJ = (NCmax + 31) / 32;
+  int ncp = (NCmax + min_pad + 3) / 4 * 4;
+  while ((C * ncp) % 16 != 0) ncp += 4;
+  p->NCP = ncp;
+  p->KP = C * ncp;
+  const int nchunks = p->KP / 16;
+  p->nchunk_t = tTmemCols / (p->NJ * 4);
+  if (p->nchunk_t > nchunks) p->nchunk_t = nchunks;
+  p->nchunk_s = nchunks - p->nchunk_t;
+  const int tail_k = p->nchunk_s * 16;
+  p->tail_stride = tail_k == 0 ? 0 : (tail_k % 32 == 16 ? tail_k : tail_k + 16);
+  const size_t smem = (size_t)(tPipes * 2 * tMB * p->KP + 32 * p->NJ * p->tail_stride) * sizeof(float) + 64;
+  return smem <= 227 * 1024;
+}
+
+// Cluster size: the smallest of {1, 2, 4, 6, 8} whose shard fits (tensor memory + the shared-memory K tail) -- 2 for
+// S = 321 / 361, 6 for S = 722 (measured: 44.2 % of peak with 6-CTA clusters and 7 x 4 tiles vs 39.5 % with 8-CTA clusters
+// and 7 x 3 tiles).  VIT_TMEM_C overrides it for experiments (any 1..8; the kernel is generic in C).
 static bool make_tmem_plan(int S, TmemPlan* p, int min_pad = 0) {
-  for (int C = 1; C <= 8; C *= 2) {
-    const int NCmax = (S + C - 1) / C;
-    if (NCmax > 32 * tMaxNJ) continue;
-    p->C = C;
-    p->base = S / C;
-    p->rem = S % C;
-    p->NCmax = NCmax;
-    p->NJ = (NCmax + 31) / 32;
-    int ncp = (NCmax + min_pad + 3) / 4 * 4;
-    while ((C * ncp) % 16 != 0) ncp += 4;
-    p->NCP = ncp;
-    p->KP = C * ncp;
-    const int nchunks = p->KP / 16;
-    p->nchunk_t = tTmemCols / (p->NJ * 4);
-    if (p->nchunk_t > nchunks) p->nchunk_t = nchunks;
-    p->nchunk_s = nchunks - p->nchunk_t;
-    const int tail_k = p->nchunk_s * 16;
-    p->tail_stride = tail_k == 0 ? 0 : (tail_k % 32 == 16 ? tail_k : tail_k + 16);
-    const size_t smem = (size_t)(tPipes * 2 * tMB * p->KP + 32 * p->NJ * p->tail_stride) * sizeof(float) + 64;
-    if (smem <= 227 * 1024) return true;
+  if (const char* e = getenv("VIT_TMEM_C")) {
+    const int C = atoi(e);
+    if (C >= 1 && C <= 8 && try_tmem_plan(S, C, p, min_pad)) return true;
   }
+  const int candidates[] = {1, 2, 4, 6, 8};
+  for (int C : candidates)
+    if (try_tmem_plan(S, C, p, min_pad)) return true;
   return false;
 }
 
