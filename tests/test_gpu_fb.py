@@ -17,8 +17,8 @@ LOGLIK_RTOL = 1e-5
 
 @pytest.fixture(scope='module', params=['tc', 'simt'])
 def FB(cuda_lib, request):
-    """Both kernels behind vit_forward_backward_f32: the tcgen05 tensor-core one (default where the shape fits) and the
-    FFMA one (VIT_FB_IMPL=simt; also the fallback for S = 722)."""
+    """Both kernels behind vit_forward_backward_f32: the tcgen05 tensor-core one (the default where the shape fits) and the
+    FFMA one (VIT_FB_IMPL=simt; also what S = 722 takes)."""
     import os
     assert torch.cuda.is_available()
     from viterbi_spl_b200 import ForwardBackward

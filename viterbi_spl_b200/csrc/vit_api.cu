@@ -71,20 +71,15 @@ bool fb_tc_supported(int S);
 size_t fb_tc_workspace_bytes(int B, int T_max, int S);
 int fb_tc_run(const float* A, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S,
               void* workspace, size_t workspace_bytes, float* gamma, float* loglik, cudaStream_t stream);
-// Which of the two forward-backward kernels runs.  VIT_FB_IMPL=tc|simt forces one (where the shape allows); otherwise the
-// cheaper one by the measured step costs (B200, S = 361): the tcgen05 kernel steps 32 clips per 3-CTA cluster in ~8.4 us
-// on 45 co-resident clusters, the FFMA kernel 14 clips per 2-CTA cluster in ~7.7 us on 74 -- so the tensor-core kernel
-// wins whenever the batch needs fewer of its rounds (1024 clips: one round each, FFMA ahead by 8 %; 4096 clips: 3 vs 4
-// rounds, tensor cores ahead by 21 %).
+// Which of the two forward-backward kernels runs: the tcgen05 tensor-core kernel wherever the shape fits (S <= 381: the
+// bf16 hi/lo image of a 127-row shard plus the accumulators must fit the 512 TMEM columns) -- measured 34.4 ms vs the
+// FFMA kernel's 46.2 ms at 1024 x 3000 x 361 and 35.0 vs 61.6 ms at 4096 x 1000 x 361 -- else the FFMA kernel (S = 722).
+// VIT_FB_IMPL=tc|simt forces one of them where the shape allows (tests run both).
 static bool fb_use_tc(int B, int S) {
+  (void)B;
   const char* e = getenv("VIT_FB_IMPL");
-  if (e && !strcmp(e, "tc")) return fb_tc_supported(S);
-  if (e && !strcmp(e, "simt")) return !fb_supported(S) && fb_tc_supported(S);
-  if (!fb_tc_supported(S)) return false;
-  if (!fb_supported(S)) return true;
-  const double cost_tc = (double)((B + 45 * 32 - 1) / (45 * 32)) * 8.4;
-  const double cost_simt = (double)((B + 74 * 14 - 1) / (74 * 14)) * 7.7;
-  return cost_tc < cost_simt;
+  if (e && !strcmp(e, "simt") && fb_supported(S)) return false;
+  return fb_tc_supported(S);
 }
 
 static int check_shape(int B, int T_max, int S) {

@@ -13,7 +13,7 @@
 //                canonical no-swizzle MN-major layout (8 x 16-byte core matrices; validated by tools/microbench_umma.cu),
 //                double buffered.  Each CTA writes the rows of its own states and pushes them to its peers with bulk
 //                async DSMEM copies that complete on the receiver's mbarrier.
-//   * D        = fp32 in TMEM; the 128 threads (thread m = row m = one state) read their row with tcgen05.ld, scale
+//   * D        = fp32 in TMEM; 256 threads (two per row = state, 16 clips each) read their row with tcgen05.ld, scale
 //                by 1/c, multiply by the emission likelihoods, store alpha~ / gamma, and write the next V.
 // One thread issues the 96 UTCHMMA of a step and commits them to an mbarrier; the step is a dependency chain
 // (wait V -> MMA -> epilogue -> exchange), so the tensor pipe is lightly used -- the point is the ~4x shorter chain than
@@ -27,7 +27,8 @@ namespace vit {
 
 constexpr int cN = 32;            // clips per cluster (N of the MMA)
 constexpr int cM = 128;           // rows of the MMA = TMEM lanes = threads
-constexpr int cThreads = 128;
+constexpr int cThreads = 256;        // two threads per row: thread (m, half) handles clips [16 half, 16 half + 16)
+constexpr int cH = cN / 2;           // clips per thread
 constexpr int cTmemCols = 512;
 
 struct TcPlan {
@@ -98,13 +99,11 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_
                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* d) {
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* d) {
   uint32_t* u = reinterpret_cast<uint32_t*>(d);
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
-                 "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
-                 "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
-                 "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+                 "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
                : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -142,11 +141,12 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
   __shared__ uint32_t s_tmem_base;
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & (cM - 1), half = tid >> 7, n0 = half * cH;     // my row (= TMEM lane) and my 16 clips
   const uint32_t C = cluster_nctarank();
   const uint32_t rank = cluster_ctarank();
   const int nc_mine = p.base + ((int)rank < p.rem ? 1 : 0);
-  const int j = (int)rank * p.base + min((int)rank, p.rem) + tid;      // my state (row tid)
-  const bool row_ok = tid < nc_mine;
+  const int j = (int)rank * p.base + min((int)rank, p.rem) + row;      // my state
+  const bool row_ok = row < nc_mine;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -164,13 +164,13 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tbase = s_tmem_base;
-  const uint32_t tlane = tbase + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
   {
     // A operand -> TMEM: hi copy in columns [0, KP/2), lo copy in [KP/2, KP); row = lane
     const int cols = KP / 2;
-#pragma unroll 1
-    for (int term = 0; term < 2; ++term) {
-      const uint4* src = reinterpret_cast<const uint4*>(packed + ((size_t)(rank * 2 + term) * cM + tid) * cols);
+    {
+      const int term = half;                               // the two thread halves fill one bf16 copy each
+      const uint4* src = reinterpret_cast<const uint4*>(packed + ((size_t)(rank * 2 + term) * cM + row) * cols);
       for (int x = 0; x < cols / 4; ++x) {
         const uint4 v = src[x];
         asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
@@ -214,20 +214,20 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
       const uint32_t cur = g & 1u, nxt = cur ^ 1u;
       const bool tail = !BWD && it == maxlen;             // forward's extra step
       // this step's likelihoods (backwards also the stored alpha~): issued first, used after the MMAs
-      float e[cN], al[cN];
+      float e[cH], al[cH];
       // lik[clip n][t][j] = p_t + n * (T_max * S): one running 64-bit pointer instead of 32 address computations
       const size_t clip_stride = (size_t)T_max * S;
       const float* p_t = lik + ((size_t)seq0 * T_max + (tail ? 0 : t)) * S + j;
       {
-        const float* pn = p_t;
+        const float* pn = p_t + (size_t)n0 * clip_stride;
 #pragma unroll
-        for (int n = 0; n < cN; ++n, pn += clip_stride) {
-          const bool lv = row_ok && !tail && t < s_len[n] && !(dev & 1);
+        for (int n = 0; n < cH; ++n, pn += clip_stride) {
+          const bool lv = row_ok && !tail && t < s_len[n0 + n] && !(dev & 1);
           e[n] = lv ? ld_global_nc_f32(pn) : 0.f;
           if (BWD) al[n] = lv ? ld_global_nc_f32(reinterpret_cast<const float*>(reinterpret_cast<const char*>(pn) + gamma_delta)) : 0.f;
         }
       }
-      float d[cN];
+      float d[cH];
       if (!first) {
         if (C > 1 && !(dev & 2)) { mbar_wait_cta(smem_u32(&s_bar[cur]), ph[cur] & 1u); ++ph[cur]; }   // peers' rows of V have landed
         if (tid == 0 && !(dev & 4)) {
@@ -264,19 +264,21 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
         }
         if (!(dev & 4)) { mbar_wait_cta(smem_u32(&s_bar[2]), n_mma & 1u); ++n_mma; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tc_ld32(tlane + KP, d);
-        if (!BWD && warp == 3) {
-          // row 127 = the ones row: c_{t-1}[n].  Lane 31 holds the 32 sums; the warp turns them into 1 / c and one CTA per
-          // cluster records them
-          if (tid == cM - 1) {
+        tc_ld16(tlane + KP + n0, d);
+        if (!BWD && (warp & 3) == 3) {
+          // row 127 = the ones row: c_{t-1}[n].  Lane 31 of warps 3 and 7 holds 16 sums each; the warp turns them into
+          // 1 / c and one CTA per cluster records them
+          if (row == cM - 1) {
 #pragma unroll
-            for (int n = 0; n < cN; ++n) s_craw[n] = d[n];
+            for (int n = 0; n < cH; ++n) s_craw[n0 + n] = d[n];
           }
           __syncwarp();
-          const int n = tid & 31;
-          const float c = s_craw[n];
-          s_c[0][n] = c > 0.f ? 1.f / c : 0.f;                        // every thread multiplies by 1 / c
-          if (rank == 0 && t - 1 < s_len[n] && !(dev & 1)) cnorm[(size_t)(seq0 + n) * T_max + (t - 1)] = c;
+          const int n = n0 + (tid & 15);
+          if ((tid & 31) < cH) {
+            const float c = s_craw[n];
+            s_c[0][n] = c > 0.f ? 1.f / c : 0.f;                      // every thread multiplies by 1 / c
+            if (rank == 0 && t - 1 < s_len[n] && !(dev & 1)) cnorm[(size_t)(seq0 + n) * T_max + (t - 1)] = c;
+          }
         }
       }
       if (BWD && first && tid < cN) s_c[0][tid] = (t < s_len[tid]) ? 1.f / cnorm[(size_t)(seq0 + tid) * T_max + t] : 1.f;
@@ -284,38 +286,38 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
       __syncthreads();                                    // s_c visible; D fully read before the next MMA batch
       if (tail) { first = false; continue; }
 
-      float v[cN];
+      float v[cH];
       {
-        float* gn = reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<float*>(p_t)) + gamma_delta);
+        float* gn = reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<float*>(p_t)) + gamma_delta) + (size_t)n0 * clip_stride;
 #pragma unroll
-        for (int n = 0; n < cN; ++n, gn += clip_stride) {
+        for (int n = 0; n < cH; ++n, gn += clip_stride) {
           if (!BWD) {
             // alpha~_t = (M alpha~_{t-1} / c_{t-1}) * b_t ;  alpha~_0 = pi * b_0
             float u;
             if (first) u = row_ok ? pi[j] : 0.f;
-            else u = d[n] * s_c[0][n];
+            else u = d[n] * s_c[0][n0 + n];
             v[n] = u * e[n];
-            if (row_ok && t < s_len[n] && !(dev & 1)) st_global_cs_f32(gn, v[n]);
+            if (row_ok && t < s_len[n0 + n] && !(dev & 1)) st_global_cs_f32(gn, v[n]);
           } else {
             // beta_t = M w_{t+1} / c_{t+1} (1 at the clip's last frame); gamma_t = alpha~_t / c_t * beta_t; w_t = b_t beta_t
-            const int len = s_len[n];
-            const float be = (t == len - 1) ? 1.f : (first ? 0.f : d[n] * s_c[1][n]);
+            const int len = s_len[n0 + n];
+            const float be = (t == len - 1) ? 1.f : (first ? 0.f : d[n] * s_c[1][n0 + n]);
             const bool lv = row_ok && t < len;
             v[n] = lv ? e[n] * be : 0.f;
-            if (lv && !(dev & 1)) st_global_cs_f32(gn, al[n] * s_c[0][n] * be);
+            if (lv && !(dev & 1)) st_global_cs_f32(gn, al[n] * s_c[0][n0 + n] * be);
           }
         }
       }
-      // my row of the next V (K position rank*NCP + tid), bf16 hi and lo: 4 core-matrix rows of 16 bytes each
+      // my half of my row of the next V (K position rank*NCP + row), bf16 hi and lo: 2 core-matrix rows of 16 bytes
       if (row_ok) {
-        const uint32_t k = rank * NCP + tid;
-        uint8_t* row = sV + nxt * buf_bytes + (k >> 3) * LBO + (k & 7) * 16;
+        const uint32_t k = rank * NCP + row;
+        uint8_t* vrow = sV + nxt * buf_bytes + (k >> 3) * LBO + (k & 7) * 16 + half * (cH / 8) * 128;
 #pragma unroll
-        for (int c8 = 0; c8 < cN / 8; ++c8) {
+        for (int c8 = 0; c8 < cH / 8; ++c8) {
           uint4 hi, lo;
           split8(v + 8 * c8, hi, lo);
-          *reinterpret_cast<uint4*>(row + c8 * 128) = hi;
-          *reinterpret_cast<uint4*>(row + term_bytes + c8 * 128) = lo;
+          *reinterpret_cast<uint4*>(vrow + c8 * 128) = hi;
+          *reinterpret_cast<uint4*>(vrow + term_bytes + c8 * 128) = lo;
         }
       }
       first = false;
