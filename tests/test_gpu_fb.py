@@ -86,6 +86,18 @@ def test_real_state_sets_softmax_style_likelihoods_ragged(FB, state_set, scaled)
     check(FB, A.astype(np.float32), pi.astype(np.float32), lik, L)
 
 
+def test_more_clips_than_one_wave_of_clusters(FB):
+    """1500 ragged clips at S = 361: more than the 45 x 32 (tensor-core kernel) / 74 x 14 (FFMA kernel) clips that are
+    co-resident, so clusters loop over several sub-batches."""
+    A, pi = hmm_params.synthetic_hmm('tonet')
+    rng = np.random.default_rng(11)
+    B, T, S = 1500, 10, 361
+    lik = np.exp(rng.standard_normal((B, T, S))).astype(np.float32)
+    L = rng.integers(0, T + 1, size=B).astype(np.int32)
+    L[::7] = T
+    check(FB, A.astype(np.float32), pi.astype(np.float32), lik, L)
+
+
 def test_long_clip_does_not_underflow(FB):
     A, pi = hmm_params.synthetic_hmm('tonet')
     rng = np.random.default_rng(3)

@@ -192,6 +192,21 @@ def test_against_oracle_ragged_real_state_sets(Decoder, state_set, kind):
         assert (p[2] == -1).all() and s[2] == -np.inf and (p[1, 1:] == -1).all()
 
 
+def test_more_clips_than_one_wave(Decoder):
+    """2100 ragged clips: more than the 74 x 14 (tmem), 33 x 32 (cluster) or 148 x 8 (banded) clips that are co-resident, so
+    the persistent CTAs loop over several sub-batches (re-armed delta buffers, barrier phases carried across)."""
+    A, pi = hmm_params.synthetic_hmm('tonet')
+    logA_T, log_pi = hmm_params.log_params(A, pi)
+    B, T, S = 2100, 20, 361
+    E = synth.batch('dyadic', B, T, S, seed0=4000)
+    L = np.random.default_rng(5).integers(0, T + 1, size=B).astype(np.int32)
+    L[::3] = T
+    want_p, want_s = c_oracle.decode_batch_c(logA_T, log_pi, E, L)
+    for algo in ('tmem', 'banded', 'cluster'):
+        p, s = Decoder(logA_T, log_pi, algo=algo).decode_host(E, L)
+        assert np.array_equal(p, want_p) and np.array_equal(s, want_s), algo
+
+
 def test_jdc_and_imm_state_sets_722(Decoder):
     for name, add_tiny in (('jdc', True), ('imm', False)):
         A, pi = hmm_params.synthetic_hmm(name)
