@@ -79,7 +79,7 @@ typedef struct vit_decode_opts {
   float* d_delta;            /* [B][T_max][S] out: the reference's T1 table (imm/tf_viterbi.py:91,94,100). */
   void* ev_forward_begin;    /* optional cudaEvent_t recorded on `stream` right before the forward (recursion) kernel */
   void* ev_forward_end;      /* optional cudaEvent_t recorded right after it (bench.py times the kernel with these) */
-  /* Frame range (VIT_ALGO_TMEM only): run the recursion over frames [frame_begin, frame_end) only; frame_end = 0
+  /* Frame range (VIT_ALGO_TMEM and VIT_ALGO_BANDED): run the recursion over frames [frame_begin, frame_end) only; frame_end = 0
    * means T_max.  A range with frame_begin > 0 resumes from the delta history that an earlier call on the SAME
    * workspace left behind, so a host can upload a long batch in time slabs and overlap each copy with the recursion
    * over the previous slab.  skip_backtrace != 0 leaves d_paths / d_scores untouched (all but the last slab). */

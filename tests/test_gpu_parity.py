@@ -319,6 +319,13 @@ def test_frame_slabs_resume_from_the_delta_history(Decoder, S, T, B, slab):
     dec = Decoder(A, pi, algo='tmem')
     p, s = dec.decode_host(E, L, slab_frames=slab)
     assert np.array_equal(p, want_p) and np.array_equal(s, want_s)
+    if S <= 384:
+        # the banded kernel resumes a frame range too (here on a banded matrix with tie-stress values)
+        Ab, pib = banded_model(S, 6, S - 1, seed=S, coarse=True)
+        want_pb, want_sb = c_oracle.decode_batch_c(Ab, pib, E, L)
+        for algo in ('banded', 'auto'):
+            pb, sb = Decoder(Ab, pib, algo=algo).decode_host(E, L, slab_frames=slab)
+            assert np.array_equal(pb, want_pb) and np.array_equal(sb, want_sb), algo
     dE, dL = torch.as_tensor(E).cuda(), torch.as_tensor(L).cuda()
     paths = scores = None
     for t0 in range(0, T, slab):
@@ -354,8 +361,12 @@ def test_device_api_lengths_and_untouched_inputs(Decoder):
     L = np.asarray([33, 5, 0, 1, 20, 33], np.int32)
     dE, dL = torch.as_tensor(E).cuda(), torch.as_tensor(L).cuda()
     keep = dE.clone()
-    from viterbi_spl_b200 import decode_batch
+    from viterbi_spl_b200 import decode_batch, ViterbiDecoder
+    out_p, out_s = torch.empty((B, T), dtype=torch.int64).pin_memory(), torch.empty((B,), dtype=torch.float32).pin_memory()
+    hp, hs = ViterbiDecoder(A, pi).decode_host(E, L, out=(out_p, out_s))       # results land in the caller's pinned buffers
+    assert np.shares_memory(hp, out_p.numpy())
     p, s = decode_batch(dE, A, pi, dL)
+    assert np.array_equal(hp, p.cpu().numpy()) and np.array_equal(hs, s.cpu().numpy())
     assert p.is_cuda and p.dtype == torch.int64 and s.dtype == torch.float32
     want_p, want_s = np_oracle.decode_batch_np(A, pi, E, L)
     assert np.array_equal(p.cpu().numpy(), want_p) and np.array_equal(s.cpu().numpy(), want_s)

@@ -63,7 +63,8 @@ bool banded_supported(int S, const vit_structure* st);
 size_t banded_workspace_bytes(int B, int T_max, int S);
 int banded_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
                   int T_max, int S, const vit_structure* st, void* workspace, size_t workspace_bytes, int64_t* paths,
-                  float* scores, float* delta_out, cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t stream);
+                  float* scores, float* delta_out, int t_begin, int t_end, bool do_backtrace, cudaEvent_t ev0,
+                  cudaEvent_t ev1, cudaStream_t stream);
 int analyze_structure(const float* A, int S, vit_structure* out);
 
 // vit_fb_tc.cu
@@ -158,11 +159,9 @@ int vit_decode_f32_ex(const float* d_logA_T, const float* d_log_pi, const float*
   float* delta_out = opts ? opts->d_delta : nullptr;
   int algo;
   const vit_structure* structure = opts ? opts->structure : nullptr;
-  const bool whole = !opts || ((opts->frame_begin == 0) && (opts->frame_end <= 0 || opts->frame_end == T_max) &&
-                               opts->skip_backtrace == 0);
   if (algo_req == VIT_ALGO_BANDED)
-    algo = (banded_supported(S, structure) && whole && !bp_out) ? (int)VIT_ALGO_BANDED : (int)VIT_ERR_UNSUPPORTED_ALGO;
-  else if (algo_req == VIT_ALGO_AUTO && whole && !bp_out && banded_supported(S, structure))
+    algo = (banded_supported(S, structure) && !bp_out) ? (int)VIT_ALGO_BANDED : (int)VIT_ERR_UNSUPPORTED_ALGO;
+  else if (algo_req == VIT_ALGO_AUTO && !bp_out && banded_supported(S, structure))
     algo = VIT_ALGO_BANDED;
   else
     algo = resolve_algo(algo_req, S, bp_out != nullptr);
@@ -177,13 +176,13 @@ int vit_decode_f32_ex(const float* d_logA_T, const float* d_log_pi, const float*
   const bool skip_bt = opts && opts->skip_backtrace != 0;
   if (algo == VIT_ALGO_BANDED)
     return banded_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, structure, d_workspace,
-                         workspace_bytes, d_paths, d_scores, delta_out, ev0, ev1, st);
+                         workspace_bytes, d_paths, d_scores, delta_out, f_begin, f_end, !skip_bt, ev0, ev1, st);
   if (algo == VIT_ALGO_TMEM) {
     // bit 3 of the S check: the shared lazy-argmax backtrace handles S <= 384, which is also the TMEM plan's limit
     return tmem_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_paths,
                        d_scores, delta_out, f_begin, f_end, !skip_bt, ev0, ev1, st);
   }
-  if (f_begin != 0 || f_end != T_max || skip_bt) return VIT_ERR_UNSUPPORTED_ALGO;   // frame ranges: VIT_ALGO_TMEM only
+  if (f_begin != 0 || f_end != T_max || skip_bt) return VIT_ERR_UNSUPPORTED_ALGO;   // frame ranges: tmem / banded only
   if (algo == VIT_ALGO_CLUSTER)
     return cluster_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes,
                           d_paths, d_scores, delta_out, ev0, ev1, st);

@@ -59,7 +59,7 @@ template <int D>
 __global__ void __launch_bounds__(bThreads, 1)
 banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict__ log_pi,
                       const float* __restrict__ log_emis, const int32_t* __restrict__ lengths, int B, int T_max, int S,
-                      int jd, float cbg, float* __restrict__ hist) {
+                      int jd, float cbg, float* __restrict__ hist, int t_begin, int t_end) {
   constexpr int W = 2 * D + 1;
   constexpr int DP = (D + 3) / 4 * 4;
   constexpr int U0 = DP - D;                         // window element of cell (r, n) = w[U0 + r + n]
@@ -118,13 +118,37 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
     // address of logE[clip][t][j0], advanced one frame per step; the history sits at a fixed distance
     const float* pe[bCPT];
 #pragma unroll
-    for (int c = 0; c < bCPT; ++c) pe[c] = log_emis + (size_t)(seq0 + c0 + c) * T_max * S + j0;
+    for (int c = 0; c < bCPT; ++c) pe[c] = log_emis + ((size_t)(seq0 + c0 + c) * T_max + t_begin) * S + j0;
     const int jd_off = jd - j0;                              // logE[..][jd] relative to pe[c]
+    const int t_stop = min(maxlen, t_end);
+    if (t_begin > 0 && t_begin < t_stop) {
+      // resume a frame range: delta_{t_begin-1} comes back from the history -- my 4 targets into the delta row, their
+      // maximum and the dense state's value into the per-warp partials the first step will combine
+      const int pb = (t_begin - 1) & 1;
+#pragma unroll
+      for (int c = 0; c < bCPT; ++c) {
+        const float* row = hist + ((size_t)(seq0 + c0 + c) * T_max + (t_begin - 1)) * S;
+        const bool lv = t_begin - 1 < len[c];
+        float v[bNJ], mloc = -INFINITY;
+#pragma unroll
+        for (int n = 0; n < bNJ; ++n) {
+          v[n] = (lv && jn_ok[n]) ? row[j0 + n] : -INFINITY;
+          mloc = fmaxf(mloc, v[n]);
+        }
+        reinterpret_cast<float4*>(s_delta[cs][pb][c] + DP)[tg] = make_float4(v[0], v[1], v[2], v[3]);
+        mloc = warp_max_f(mloc);
+        if (lane == 0) {
+          s_partM[cs][pb][tgw][c] = mloc;
+          s_partD[cs][pb][tgw][c] = (lv && jd >= 0) ? row[jd] : -INFINITY;      // + ed_prev (= 0) gives delta[jd] back
+        }
+      }
+      bpipe_bar_sync(cs);
+    }
 
     float ed_prev[bCPT];                                     // logE[t-1][jd] of my clips
 #pragma unroll
     for (int c = 0; c < bCPT; ++c) ed_prev[c] = 0.f;
-    for (int t = 0; t < maxlen; ++t) {
+    for (int t = t_begin; t < t_stop; ++t) {
       const int buf = t & 1;
       // keep the two running pointers in registers (ptxas would otherwise re-derive the 64-bit address of every load)
 #pragma unroll
@@ -163,7 +187,7 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
           float dm = fmaxf(fmaxf(pm[0], pm[bCPT]), pm[2 * bCPT]);
           xd[c] = (jd >= 0) ? __fadd_rn(fmaxf(fmaxf(pdd[0], pdd[bCPT]), pdd[2 * bCPT]), ed_prev[c]) : -INFINITY;
           dm = fmaxf(dm, xd[c]);
-          if (jd >= 0 && tgw == 0 && lane == 0 && t - 1 < len[c])
+          if (jd >= 0 && tgw == 0 && lane == 0 && t - 1 < len[c] && t - 1 >= t_begin)
             st_global_cs_f32(hist + ((size_t)(seq0 + c0 + c) * T_max + (t - 1)) * S + jd, xd[c]);
           // background term fl(max_i delta_i + c) and the dense source column
           const float bg = __fadd_rn(dm, cbg);
@@ -231,14 +255,14 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
       bpipe_bar_sync(cs);
     }
     // the dense state's value of the last frame
-    if (jd >= 0 && maxlen > 0 && tgw == 0 && lane == 0) {
-      const int buf = (maxlen - 1) & 1;
+    if (jd >= 0 && t_stop > t_begin && tgw == 0 && lane == 0) {
+      const int buf = (t_stop - 1) & 1;
 #pragma unroll
       for (int c = 0; c < bCPT; ++c) {
-        if (len[c] == maxlen) {
+        if (t_stop - 1 < len[c]) {
           const float* pdd = &s_partD[cs][buf][0][c];
           const float x = __fadd_rn(fmaxf(fmaxf(pdd[0], pdd[bCPT]), pdd[2 * bCPT]), ed_prev[c]);
-          st_global_cs_f32(hist + ((size_t)(seq0 + c0 + c) * T_max + (maxlen - 1)) * S + jd, x);
+          st_global_cs_f32(hist + ((size_t)(seq0 + c0 + c) * T_max + (t_stop - 1)) * S + jd, x);
         }
       }
     }
@@ -268,8 +292,11 @@ size_t banded_workspace_bytes(int B, int T_max, int S) {
 
 int banded_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
                   int T_max, int S, const vit_structure* st, void* workspace, size_t workspace_bytes, int64_t* paths,
-                  float* scores, float* delta_out, cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t stream) {
+                  float* scores, float* delta_out, int t_begin, int t_end, bool do_backtrace, cudaEvent_t ev0,
+                  cudaEvent_t ev1, cudaStream_t stream) {
   if (!banded_supported(S, st)) return VIT_ERR_UNSUPPORTED_ALGO;
+  if (t_end > T_max) t_end = T_max;
+  if (t_begin < 0 || t_begin > t_end) return VIT_ERR_INVALID_ARGUMENT;
   if (!delta_out && workspace_bytes < banded_workspace_bytes(B, T_max, S)) return VIT_ERR_WORKSPACE_TOO_SMALL;
   if (B == 0) return VIT_OK;
   float* hist = delta_out ? delta_out : (float*)workspace;
@@ -283,7 +310,8 @@ int banded_decode(const float* logA_T, const float* log_pi, const float* log_emi
 #define VIT_BANDED_CASE(DD)                                                                                          \
   case DD: {                                                                                                         \
     banded_forward_kernel<DD><<<grid, bThreads, 0, stream>>>(logA_T, log_pi, log_emis, lengths, B, T_max, S,         \
-                                                              st->dense_index, st->background, hist);               \
+                                                              st->dense_index, st->background, hist, t_begin,       \
+                                                              t_end);                                                \
   } break;
   switch (D) {
     VIT_BANDED_CASE(4) VIT_BANDED_CASE(8) VIT_BANDED_CASE(12) VIT_BANDED_CASE(14)
@@ -293,6 +321,7 @@ int banded_decode(const float* logA_T, const float* log_pi, const float* log_emi
   note_launch();
   VIT_CUDA_TRY(cudaGetLastError());
   if (ev1) VIT_CUDA_TRY(cudaEventRecord(ev1, stream));
+  if (!do_backtrace) return VIT_OK;
   return launch_hist_backtrace(logA_T, hist, lengths, B, T_max, S, paths, scores, stream);
 }
 

@@ -71,7 +71,7 @@ class ViterbiDecoder:
         torch.cuda.Event(enable_timing=True) recorded by the library around the forward kernel.
         frame_range=(t0, t1) runs the recursion over those frames only, resuming (t0 > 0) from the delta history the
         previous call left in this decoder's workspace; backtrace=False skips the backtrace (all but the last range).
-        Frame ranges need the tmem algorithm.
+        Frame ranges need the tmem or the banded algorithm.
         backtrace_stream: run the backtrace on that stream (ordered after the forward kernel) so that the next decode
         on `stream` overlaps it; the caller then owns the synchronisation (see PipelinedDecoder) and must give
         consecutive calls different `workspace_slot`s."""
@@ -128,19 +128,24 @@ class ViterbiDecoder:
         return buf[:n].view(*shape)
 
     def supports_frame_slabs(self):
-        """True if this decoder's algorithm can run the recursion as consecutive frame ranges (tmem)."""
+        """True if this decoder's algorithm can run the recursion as consecutive frame ranges (tmem, banded)."""
         algo = self.algo
         if algo == _lib.ALGO_AUTO:
-            algo = self.lib.vit_select_algo(1, 1, self.S)
+            algo = self.lib.vit_select_algo(1, 1, self.S)      # (auto takes the banded kernel where the matrix allows)
+        if algo == _lib.ALGO_BANDED:
+            return self.structure.kind == 1
         return algo == _lib.ALGO_TMEM
 
-    def decode_host(self, log_emis, lengths=None, slab_frames=None):
+    def decode_host(self, log_emis, lengths=None, slab_frames=None, out=None):
         """log_emis: host float32 array [B, T, S] (NumPy or CPU tensor).  Copies host->device, decodes, copies the
         paths and scores back; returns NumPy (paths int64 [B, T], scores float32 [B]).
 
         Large batches are uploaded in time slabs of `slab_frames` frames (default: about T/16 once the batch exceeds
         64 MB) on a copy stream while the recursion over the previous slab runs on the compute stream, so the
-        end-to-end time is max(PCIe copy, decode) instead of their sum."""
+        end-to-end time is max(PCIe copy, decode) instead of their sum.  (Measured on B200: 16 slabs of a 4.4 GB batch
+        upload at the full 55 GB/s; 32 slabs -- 136 KB rows -- drop to 35 GB/s.)
+        out=(paths, scores): optional page-locked CPU tensors (int64 [B, T], float32 [B]) that receive the results
+        directly; they are returned as NumPy views, which saves a 25 MB host copy per 1024 x 3000 batch."""
         E = torch.as_tensor(log_emis)
         assert E.dtype == torch.float32 and E.ndim == 3
         B, T, S = E.shape
@@ -160,11 +165,18 @@ class ViterbiDecoder:
                 paths, scores = self.decode_device(dE, dL)
             else:
                 paths, scores = self._decode_host_slabs(src, dL, int(slab_frames))
-            hp = self._pinned_buf('paths', (B, T), torch.int64)
-            hs = self._pinned_buf('scores', (B,), torch.float32)
+            if out is not None:
+                hp, hs = out
+                assert hp.is_pinned() and hs.is_pinned() and hp.shape == (B, T) and hs.shape == (B,)
+                assert hp.dtype == torch.int64 and hs.dtype == torch.float32
+            else:
+                hp = self._pinned_buf('paths', (B, T), torch.int64)
+                hs = self._pinned_buf('scores', (B,), torch.float32)
             hp.copy_(paths, non_blocking=True)
             hs.copy_(scores, non_blocking=True)
             torch.cuda.current_stream().synchronize()
+        if out is not None:
+            return hp.numpy(), hs.numpy()
         return hp.numpy().copy(), hs.numpy().copy()
 
     def _decode_host_slabs(self, src, dL, slab):
