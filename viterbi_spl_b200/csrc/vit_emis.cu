@@ -63,20 +63,52 @@ template <int MODEL, bool SPW5>
 __global__ void __launch_bounds__(32 * kEmisWarps)
 emissions_kernel(const float* __restrict__ logits, const float* __restrict__ prior, long long n_frames, int n_bins, int spw,
                  float threshold, int out_log, float* __restrict__ out) {
-  extern __shared__ float s_x[];                                     // [kEmisWarps][3][n_bins + 16] (SPW5) or [.][n_bins]
+  extern __shared__ float s_x[];                                     // [kEmisWarps][5][n_bins + 16]: x, m2, m4, peak idx, peak exp
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int np = n_bins + 16;                                        // padded row: 5 + n_bins + 5, rounded up
-  float* x = SPW5 ? s_x + (size_t)w * 3 * np + 5 : s_x + (size_t)w * n_bins;   // x[k] = logit of bin k; x[-5 .. n+4] valid
-  float* m2 = s_x + (size_t)w * 3 * np + np + 5;
-  float* m4 = s_x + (size_t)w * 3 * np + 2 * np + 5;
+  float* x = s_x + (size_t)w * 5 * np + 5;                           // x[k] = logit of bin k; x[-5 .. n+4] valid
+  float* m2 = s_x + (size_t)w * 5 * np + np + 5;
+  float* m4 = s_x + (size_t)w * 5 * np + 2 * np + 5;
+  int* pk_idx = reinterpret_cast<int*>(s_x + (size_t)w * 5 * np + 3 * np);     // compacted peak bins
+  float* pk_e = s_x + (size_t)w * 5 * np + 4 * np;                   // exp(peak logit - max)
   const int n_in = MODEL == 0 ? n_bins + 1 : n_bins;
   const int S = n_bins + 1;
   const float zero_out = out_log ? logf(kTinyF) : 0.f;               // log(0 + tiny) = -87.33655
-  for (long long f = (long long)blockIdx.x * kEmisWarps + w; f < n_frames; f += (long long)gridDim.x * kEmisWarps) {
+  // software pipeline over frames: the next frame's logits are fetched into registers (n_bins <= 384) before this frame
+  // is processed, so the HBM latency hides under ~700 instructions of work instead of stalling every frame
+  constexpr int kPre = 12;
+  const bool use_pre = n_bins <= 32 * kPre;
+  const long long f_stride = (long long)gridDim.x * kEmisWarps;
+  float pre[kPre];
+  float pre_unv = 0.f;
+  {
+    const long long f0 = (long long)blockIdx.x * kEmisWarps + w;
+    if (use_pre && f0 < n_frames) {
+      const float* in0 = logits + f0 * n_in;
+#pragma unroll
+      for (int i = 0; i < kPre; ++i) pre[i] = (lane + 32 * i < n_bins) ? ld_global_nc_f32(in0 + (MODEL == 0 ? 1 : 0) + lane + 32 * i) : 0.f;
+      if (MODEL == 0) pre_unv = ld_global_nc_f32(in0);
+    }
+  }
+  for (long long f = (long long)blockIdx.x * kEmisWarps + w; f < n_frames; f += f_stride) {
     const float* in = logits + f * n_in;
     float* o = out + f * S;
     const float* vin = in + (MODEL == 0 ? 1 : 0);
-    for (int k = lane; k < n_bins; k += 32) x[k] = vin[k];
+    float unv_now = 0.f;
+    if (use_pre) {
+#pragma unroll
+      for (int i = 0; i < kPre; ++i) if (lane + 32 * i < n_bins) x[lane + 32 * i] = pre[i];
+      unv_now = pre_unv;
+      if (f + f_stride < n_frames) {
+        const float* in1 = logits + (f + f_stride) * n_in;
+#pragma unroll
+        for (int i = 0; i < kPre; ++i) pre[i] = (lane + 32 * i < n_bins) ? ld_global_nc_f32(in1 + (MODEL == 0 ? 1 : 0) + lane + 32 * i) : 0.f;
+        if (MODEL == 0) pre_unv = ld_global_nc_f32(in1);
+      }
+    } else {
+      for (int k = lane; k < n_bins; k += 32) x[k] = vin[k];
+      if (MODEL == 0) unv_now = in[0];
+    }
     if (SPW5) {
       __syncwarp();
       if (lane < 5) {                                                // np.pad(mode='reflect'): -m -> m, n-1+m -> n-1-m
@@ -89,32 +121,40 @@ emissions_kernel(const float* __restrict__ logits, const float* __restrict__ pri
       for (int k = lane - 5; k < n_bins + 2; k += 32) m4[k] = fmaxf(m2[k], m2[k + 2]);         // max of x[k .. k+3]
     }
     __syncwarp();
-    // pass 1: peak flags of my bins (bit i <-> bin lane + 32 i), maximum peak logit
-    float mx = -INFINITY;
-    uint32_t mask = 0;
-    for (int k = lane, i = 0; k < n_bins; k += 32, ++i) {
-      bool pk;
-      if (SPW5) {
-        const float c = x[k];
-        pk = (c > fmaxf(m4[k - 5], x[k - 1])) && (c >= fmaxf(m4[k + 1], x[k + 5]));
-      } else {
-        pk = is_peak(x, n_bins, k, spw);
+    // pass 1: find the peaks and COMPACT them (ballot + prefix count) into a per-warp list, so that the expensive
+    // exp / log below run once per peak on consecutive lanes instead of once per bin under divergence
+    int cnt = 0;                                                     // number of voiced peaks (warp-uniform)
+    for (int k = lane; k < ((n_bins + 31) & ~31); k += 32) {
+      bool pk = false;
+      if (k < n_bins) {
+        if (SPW5) {
+          const float c = x[k];
+          pk = (c > fmaxf(m4[k - 5], x[k - 1])) && (c >= fmaxf(m4[k + 1], x[k + 5]));
+        } else {
+          pk = is_peak(x, n_bins, k, spw);
+        }
       }
-      if (pk) {
-        mx = fmaxf(mx, x[k]);
-        mask |= 1u << i;
-      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, pk);
+      if (pk) pk_idx[cnt + __popc(bal & ((1u << lane) - 1u))] = k;
+      cnt += __popc(bal);
     }
-    const int n_peaks = __reduce_add_sync(0xffffffffu, __popc(mask));
+    __syncwarp();
+    const int n_peaks = cnt;
+    float mx = -INFINITY;
+    for (int q = lane; q < cnt; q += 32) mx = fmaxf(mx, x[pk_idx[q]]);
     float unv_logit = 0.f;
     if (MODEL == 0) {
-      unv_logit = in[0];                                             // column 0 is always a peak (:2521)
+      unv_logit = unv_now;                                           // column 0 is always a peak (:2521)
       mx = fmaxf(mx, unv_logit);
     }
     mx = warp_max(mx);
-    // pass 2: sum of exp(peak - max)
+    // pass 2: exp(peak - max), kept for pass 3, and their sum
     float sum = 0.f;
-    for (uint32_t mm = mask; mm; mm &= mm - 1) sum += expf(x[lane + 32 * (__ffs(mm) - 1)] - mx);
+    for (int q = lane; q < cnt; q += 32) {
+      const float e = expf(x[pk_idx[q]] - mx);
+      pk_e[q] = e;
+      sum += e;
+    }
     sum = warp_sum(sum);
     float unv_out;
     float scale;                                                     // value of a voiced peak = exp(x - mx) * scale / prior
@@ -138,21 +178,24 @@ emissions_kernel(const float* __restrict__ logits, const float* __restrict__ pri
         unv_out = qv;
       }
     }
-    // pass 3: write the row (coalesced); non-peaks are exactly 0 -> log(tiny)
-    for (int k = lane, i = 0; k < n_bins; k += 32, ++i) {
-      float v = zero_out;
-      if ((mask >> i) & 1u) {
-        float p = expf(x[k] - mx);
-        if (MODEL == 0) {
-          p = p / sum;                                               // np.divide(peak_logits, t) then / priors (:2568-2572)
-          if (prior) p = p / prior[k + 1];
-        } else {
-          p = p * scale;                                             // t = p_voiced / sum; peak_logits * t (:1777-1778)
-        }
-        v = out_log ? logf(p + kTinyF) : p;
+    // pass 3: the output row is assembled in shared memory (x is dead now): constant fill, peaks scattered over it,
+    // then one coalesced copy.  Non-peaks are exactly 0 -> log(tiny).
+    __syncwarp();
+    for (int k = lane; k < n_bins; k += 32) x[k] = zero_out;
+    __syncwarp();
+    for (int q = lane; q < cnt; q += 32) {
+      const int k = pk_idx[q];
+      float p = pk_e[q];
+      if (MODEL == 0) {
+        p = p / sum;                                                 // np.divide(peak_logits, t) then / priors (:2568-2572)
+        if (prior) p = p / prior[k + 1];
+      } else {
+        p = p * scale;                                               // t = p_voiced / sum; peak_logits * t (:1777-1778)
       }
-      o[k] = v;
+      x[k] = out_log ? logf(p + kTinyF) : p;
     }
+    __syncwarp();
+    for (int k = lane; k < n_bins; k += 32) o[k] = x[k];
     if (lane == 0) o[n_bins] = out_log ? logf(unv_out + kTinyF) : unv_out;
     __syncwarp();
   }
@@ -176,7 +219,7 @@ int emissions_run(const float* logits, const float* prior, int B, int T, int n_b
   if (n_bins > 1024) return VIT_ERR_UNSUPPORTED_ALGO;                 // 32 peak flags per lane
   if (model != 0 && model != 1) return VIT_ERR_INVALID_ARGUMENT;
   const bool fast = spw == 5 && n_bins >= 7;
-  const size_t smem = fast ? (size_t)kEmisWarps * 3 * (n_bins + 16) * sizeof(float) : (size_t)kEmisWarps * n_bins * sizeof(float);
+  const size_t smem = (size_t)kEmisWarps * 5 * (n_bins + 16) * sizeof(float);
   int num_sms = 148, dev = 0;
   VIT_CUDA_TRY(cudaGetDevice(&dev));
   VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
