@@ -192,6 +192,31 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
   const uint32_t tx_bytes = (C - 1) * 2 * slice_bytes;
   const long long gamma_delta = reinterpret_cast<const char*>(gamma) - reinterpret_cast<const char*>(lik);
 
+  // tcgen05.mma over K blocks [kb0, kb1) of V buffer `vbuf`: four bf16 products per block (hi.hi, hi.lo, lo.hi, lo.lo;
+  // without lo.lo the gamma error reaches 1.03e-4, measured).  Descriptor = start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 |
+  // version 1 << 46; a K block of 16 advances the start field by 2 LBO >> 4 (the smem window is < 256 KB: no carry).
+  auto issue_mma = [&](uint32_t vbuf, int kb0, int kb1, uint32_t acc) {
+    const uint32_t vb = smem_u32(sV) + vbuf * buf_bytes;
+    const uint32_t desc_hi32 = (128u >> 4) | (1u << 14);
+    uint32_t lo_hi = (((vb >> 4) & 0x3FFF) | (((LBO >> 4) & 0x3FFF) << 16)) + kb0 * ((2 * LBO) >> 4);
+    uint32_t lo_lo = ((((vb + term_bytes) >> 4) & 0x3FFF) | (((LBO >> 4) & 0x3FFF) << 16)) + kb0 * ((2 * LBO) >> 4);
+    uint32_t a_hi = tbase + kb0 * 8, a_lo = tbase + KP / 2 + kb0 * 8;
+#pragma unroll 4
+    for (int kb = kb0; kb < kb1; ++kb) {
+      const uint64_t desc_hi = ((uint64_t)desc_hi32 << 32) | lo_hi;
+      const uint64_t desc_lo = ((uint64_t)desc_hi32 << 32) | lo_lo;
+      tc_mma(d_tmem, a_hi, desc_hi, idesc, acc);
+      acc = 1;
+      tc_mma(d_tmem, a_hi, desc_lo, idesc, 1);
+      tc_mma(d_tmem, a_lo, desc_hi, idesc, 1);
+      tc_mma(d_tmem, a_lo, desc_lo, idesc, 1);
+      lo_hi += (2 * LBO) >> 4;
+      lo_lo += (2 * LBO) >> 4;
+      a_hi += 8;
+      a_lo += 8;
+    }
+  };
+
   uint32_t g = 0;           // the MMA of iteration g reads V buffer g & 1; the epilogue writes buffer (g + 1) & 1
   uint32_t ph[2] = {0, 0};  // completed phases of the two "V rows have landed" barriers
   uint32_t n_mma = 0;       // MMA batches committed so far (parity of s_bar[2])
@@ -231,30 +256,12 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
       if (!first) {
         if (C > 1 && !(dev & 2)) { mbar_wait_cta(smem_u32(&s_bar[cur]), ph[cur] & 1u); ++ph[cur]; }   // peers' rows of V have landed
         if (tid == 0 && !(dev & 4)) {
+          // the K blocks of my own rows were issued at the end of the previous iteration (see below); now that the
+          // peers' rows have landed, the other shards' K blocks follow and the batch is committed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t vb = smem_u32(sV) + cur * buf_bytes;
-          // descriptor = start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46; a K block of 16 advances the
-          // start field by 2 LBO >> 4 (the smem window is < 256 KB, so the 14-bit field never carries)
-          const uint32_t desc_hi32 = (128u >> 4) | (1u << 14);
-          uint32_t lo_hi = ((vb >> 4) & 0x3FFF) | (((LBO >> 4) & 0x3FFF) << 16);
-          uint32_t lo_lo = (((vb + term_bytes) >> 4) & 0x3FFF) | (((LBO >> 4) & 0x3FFF) << 16);
-          uint32_t a_hi = tbase, a_lo = tbase + KP / 2;
-          const int nkb = KP / 16;
-          uint32_t acc = 0;
-#pragma unroll 4
-          for (int kb = 0; kb < nkb; ++kb) {
-            const uint64_t desc_hi = ((uint64_t)desc_hi32 << 32) | lo_hi;
-            const uint64_t desc_lo = ((uint64_t)desc_hi32 << 32) | lo_lo;
-            tc_mma(d_tmem, a_hi, desc_hi, idesc, acc);
-            acc = 1;
-            tc_mma(d_tmem, a_hi, desc_lo, idesc, 1);
-            tc_mma(d_tmem, a_lo, desc_hi, idesc, 1);
-            tc_mma(d_tmem, a_lo, desc_lo, idesc, 1);     // without lo.lo the gamma error reaches 1.03e-4 (measured)
-            lo_hi += (2 * LBO) >> 4;
-            lo_lo += (2 * LBO) >> 4;
-            a_hi += 8;
-            a_lo += 8;
-          }
+          const int own0 = (int)rank * NCP / 16, own1 = own0 + NCP / 16;
+          issue_mma(cur, 0, own0, 1);
+          issue_mma(cur, own1, KP / 16, 1);
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar[2])) : "memory");
         }
         if (BWD && tid < 2 * cN) {
@@ -323,6 +330,12 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
       first = false;
       fence_proxy_async_smem();
       __syncthreads();
+      // my own rows of the next V are complete: start the next step's GEMM on their K blocks now (accumulator reset),
+      // under the exchange with the peers.  Every thread has read D (tcgen05.ld completed before the barrier above).
+      if (tid == 0 && !(dev & 4) && it + 1 < n_iter) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_mma(nxt, (int)rank * NCP / 16, (int)rank * NCP / 16 + NCP / 16, 0);
+      }
       if (C > 1 && !(dev & 2)) {
         if (tid == 0) mbar_arrive_expect_tx(smem_u32(&s_bar[nxt]), tx_bytes);
         if (tid < (int)(C - 1) * 2) {
