@@ -21,7 +21,7 @@ A, pi = hmm_params.synthetic_hmm('tonet' if S == 361 else 'dcnet')
 logA_T, log_pi = hmm_params.log_params(A, pi)
 E = synth.device_dense_softmax(1, T, S, seed=5, device=torch.device('cuda'))
 out = {'frames': T, 'states': S}
-for algo in ('tmem', 'cluster'):
+for algo in ('tmem', 'auto'):
     dec = ViterbiDecoder(logA_T, log_pi, algo=algo)
     p, s = dec.decode_device(E)
     torch.cuda.synchronize()
@@ -33,7 +33,8 @@ for algo in ('tmem', 'cluster'):
     if algo == 'tmem':
         p_t, s_t = p.clone(), s.clone()
     else:
-        out['tmem_equals_cluster'] = bool(torch.equal(p, p_t) and torch.equal(s, s_t))
+        out['auto_is'] = 'banded' if dec.structure.kind == 1 else 'tmem'
+        out['tmem_equals_auto'] = bool(torch.equal(p, p_t) and torch.equal(s, s_t))
     del dec
 if a.check:
     from oracle import c_oracle
