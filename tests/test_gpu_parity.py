@@ -213,7 +213,8 @@ def test_jdc_and_imm_state_sets_722(Decoder):
         logA_T, log_pi = hmm_params.log_params(A, pi, add_tiny=add_tiny)
         E = synth.batch('dense_softmax', 5, 50, 722, seed0=5)
         want_p, want_s = c_oracle.decode_batch_c(logA_T, log_pi, E)
-        for algo in ('auto', 'tmem', 'backpointer'):
+        # auto: the jdc matrix (band +-40) takes the wide banded kernel, the dense imm matrix the tmem kernel
+        for algo in ('auto', 'tmem', 'backpointer') + (('banded',) if name == 'jdc' else ()):
             p, s = Decoder(logA_T, log_pi, algo=algo).decode_host(E)
             assert np.array_equal(p, want_p) and np.array_equal(s, want_s), (name, algo)
 
@@ -266,7 +267,10 @@ def banded_model(S, d, dense, seed, coarse, background=-87.33655):
 
 @pytest.mark.parametrize('S,d,dense,T,B', [(361, 14, 360, 90, 19), (321, 12, 320, 70, 9), (361, 14, 0, 40, 8), (97, 3, 50, 60, 5),
                                            (384, 14, 383, 25, 17), (5, 1, None, 30, 3), (64, 0, None, 20, 9), (200, 8, 17, 33, 11),
-                                           (130, 13, None, 260, 4), (33, 4, 32, 1, 2)])
+                                           (130, 13, None, 260, 4), (33, 4, 32, 1, 2),
+                                           # wide bands / 722-state sets: the tensor-memory variant
+                                           (722, 40, 721, 40, 9), (722, 33, 0, 25, 5), (500, 20, 250, 30, 12),
+                                           (96, 28, None, 50, 4), (768, 40, 767, 12, 3), (384, 15, 383, 20, 10)])
 @pytest.mark.parametrize('coarse', [False, True])
 def test_banded_fast_path_is_bit_identical(Decoder, S, d, dense, T, B, coarse):
     """VIT_ALGO_BANDED (S (2d+2) cells per frame) against the oracle and the dense kernels, including tie-stress
@@ -319,9 +323,10 @@ def test_frame_slabs_resume_from_the_delta_history(Decoder, S, T, B, slab):
     dec = Decoder(A, pi, algo='tmem')
     p, s = dec.decode_host(E, L, slab_frames=slab)
     assert np.array_equal(p, want_p) and np.array_equal(s, want_s)
-    if S <= 384:
-        # the banded kernel resumes a frame range too (here on a banded matrix with tie-stress values)
-        Ab, pib = banded_model(S, 6, S - 1, seed=S, coarse=True)
+    if S <= 384 or S % 2 == 0:
+        # the banded kernels resume a frame range too (here on a banded matrix with tie-stress values; S = 722 takes the
+        # tensor-memory variant)
+        Ab, pib = banded_model(S, 6 if S <= 384 else 30, S - 1, seed=S, coarse=True)
         want_pb, want_sb = c_oracle.decode_batch_c(Ab, pib, E, L)
         for algo in ('banded', 'auto'):
             pb, sb = Decoder(Ab, pib, algo=algo).decode_host(E, L, slab_frames=slab)

@@ -18,10 +18,10 @@ def test_reference_state_sets(cuda_lib):
         logA_T, _ = hmm_params.log_params(A, pi)
         kind, hw, di, bg = analyze(cuda_lib, logA_T)
         assert (kind, hw, di) == (1, d, S - 1) and bg == log_tiny
-    # jdc: band +-40 of 722 states -- too wide / too many states for the register-resident kernel
+    # jdc: band +-40 of 722 states -- the tensor-memory variant of the banded kernel takes it
     A, pi = hmm_params.synthetic_hmm('jdc')
     kind, hw, di, bg = analyze(cuda_lib, hmm_params.log_params(A, pi)[0])
-    assert kind == 0 and hw == 40 and di == 721
+    assert kind == 1 and hw == 40 and di == 721
     # imm: fully dense
     A, pi = hmm_params.synthetic_hmm('imm')
     kind, hw, di, bg = analyze(cuda_lib, hmm_params.log_params(A, pi, add_tiny=False)[0])
@@ -41,10 +41,22 @@ def test_hand_made_matrices(cuda_lib):
     assert analyze(cuda_lib, B) == (1, 3, 7, -50.0)
     C = A.copy()
     C[0, S - 1] = -1.0                                     # one far entry, not a dense state: the band must cover it
-    assert analyze(cuda_lib, C)[0] == 0
+    assert analyze(cuda_lib, C)[:2] == (1, S - 1)          # (39 <= 40: the wide kernel's band spans the whole 40 x 40 matrix)
+    S3 = 100
+    C3 = np.full((S3, S3), -50.0, np.float32)
+    C3[np.arange(S3), np.arange(S3)] = -1.0
+    C3[0, S3 - 1] = -1.0
+    assert analyze(cuda_lib, C3)[:2] == (0, S3 - 1)        # a band of 99 is no structure at all
     D = np.full((S, S), -np.inf, np.float32)
     D[np.arange(S), np.arange(S)] = 0
     assert analyze(cuda_lib, D) == (1, 0, -1, -np.inf)
     E = A.copy()
     E[3, 3] = np.nan
     assert analyze(cuda_lib, E)[0] == 0
+    # band of 41: too wide for either kernel; band of 20 on an odd state count: the wide kernel wants even S
+    for S2, d2, want in ((200, 41, 0), (200, 20, 1), (201, 20, 0), (201, 14, 1)):
+        F = np.full((S2, S2), -9.0, np.float32)
+        for k in range(-d2, d2 + 1):
+            idx = np.arange(max(0, -k), min(S2, S2 - k))
+            F[idx, idx + k] = -1.0
+        assert analyze(cuda_lib, F)[:2] == (want, d2), (S2, d2)

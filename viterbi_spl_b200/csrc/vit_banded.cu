@@ -279,15 +279,27 @@ static int banded_template_D(int d) {
   return -1;
 }
 
-bool banded_supported(int S, const vit_structure* st) {
+// vit_banded_wide.cu: band entries in tensor memory (S <= 768, d <= 40)
+bool banded_wide_supported(int S, const vit_structure* st);
+int banded_wide_forward(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
+                        int T_max, int S, const vit_structure* st, void* packed_ws, float* hist, int t_begin, int t_end,
+                        cudaStream_t stream);
+constexpr size_t kWidePackedBytes = 128 * 512 * sizeof(float);
+
+static bool banded_narrow_supported(int S, const vit_structure* st) {
   if (!st || st->kind != 1) return false;
   if (S > bMaxS || S < 2) return false;
   if (st->dense_index < -1 || st->dense_index >= S) return false;
   return banded_template_D(st->halfwidth) > 0;
 }
 
+bool banded_supported(int S, const vit_structure* st) {
+  if (!st || st->kind != 1) return false;
+  return banded_narrow_supported(S, st) || banded_wide_supported(S, st);
+}
+
 size_t banded_workspace_bytes(int B, int T_max, int S) {
-  return align_up((size_t)B * T_max * S * sizeof(float), 256);                   // delta history (T1 table)
+  return align_up(kWidePackedBytes, 256) + align_up((size_t)B * T_max * S * sizeof(float), 256);   // TMEM image + T1 table
 }
 
 int banded_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
@@ -299,7 +311,18 @@ int banded_decode(const float* logA_T, const float* log_pi, const float* log_emi
   if (t_begin < 0 || t_begin > t_end) return VIT_ERR_INVALID_ARGUMENT;
   if (!delta_out && workspace_bytes < banded_workspace_bytes(B, T_max, S)) return VIT_ERR_WORKSPACE_TOO_SMALL;
   if (B == 0) return VIT_OK;
-  float* hist = delta_out ? delta_out : (float*)workspace;
+  float* hist = delta_out ? delta_out : (float*)((char*)workspace + align_up(kWidePackedBytes, 256));
+  if (!banded_narrow_supported(S, st)) {
+    // wide bands / 722-state sets: band entries in tensor memory
+    if (workspace_bytes < align_up(kWidePackedBytes, 256)) return VIT_ERR_WORKSPACE_TOO_SMALL;
+    if (ev0) VIT_CUDA_TRY(cudaEventRecord(ev0, stream));
+    const int rc = banded_wide_forward(logA_T, log_pi, log_emis, lengths, B, T_max, S, st, workspace, hist, t_begin, t_end,
+                                       stream);
+    if (rc != VIT_OK) return rc;
+    if (ev1) VIT_CUDA_TRY(cudaEventRecord(ev1, stream));
+    if (!do_backtrace) return VIT_OK;
+    return launch_hist_backtrace(logA_T, hist, lengths, B, T_max, S, paths, scores, stream);
+  }
   const int D = banded_template_D(st->halfwidth);
   int num_sms = 148, dev = 0;
   VIT_CUDA_TRY(cudaGetDevice(&dev));
@@ -327,7 +350,8 @@ int banded_decode(const float* logA_T, const float* log_pi, const float* log_emi
 
 // Host-side structure analysis (h_logA_T is a HOST pointer).  kind = 1 iff, apart from at most one state that is both
 // a dense source column and a dense target row, every entry that differs from the minimum entry c lies within
-// |i - j| <= halfwidth and the band is narrow enough for the register-resident kernel.
+// |i - j| <= halfwidth and one of the two banded kernels takes the shape (S <= 384 with d <= 14: band in registers;
+// even S <= 768 with d <= 40: band in tensor memory).
 int analyze_structure(const float* A, int S, vit_structure* out) {
   out->kind = 0;
   out->halfwidth = 0;
@@ -362,7 +386,8 @@ int analyze_structure(const float* A, int S, vit_structure* out) {
   out->background = c;
   out->halfwidth = d;
   out->dense_index = di;
-  out->kind = (S <= bMaxS && banded_template_D(d) > 0) ? 1 : 0;
+  out->kind = 1;
+  out->kind = (banded_narrow_supported(S, out) || banded_wide_supported(S, out)) ? 1 : 0;
   return VIT_OK;
 }
 
