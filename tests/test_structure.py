@@ -44,8 +44,10 @@ def test_hand_made_matrices(cuda_lib):
     assert analyze(cuda_lib, C)[:2] == (1, S - 1)          # (39 <= 40: the wide kernel's band spans the whole 40 x 40 matrix)
     S3 = 100
     C3 = np.full((S3, S3), -50.0, np.float32)
-    C3[np.arange(S3), np.arange(S3)] = -1.0
-    C3[0, S3 - 1] = -1.0
+    for k in (-1, 0, 1):
+        idx = np.arange(max(0, -k), min(S3, S3 - k))
+        C3[idx, idx + k] = -1.0
+    C3[0, S3 - 1] = -1.0                                   # (on a bare diagonal state 0 would be taken as the dense state)
     assert analyze(cuda_lib, C3)[:2] == (0, S3 - 1)        # a band of 99 is no structure at all
     D = np.full((S, S), -np.inf, np.float32)
     D[np.arange(S), np.arange(S)] = 0
