@@ -56,8 +56,9 @@ typedef enum vit_algo {
    * shard; 7 clips x 6 targets per thread, two pipelines per CTA.  S <= 384.  Supports frame ranges. */
   VIT_ALGO_TMEM = 3,
   /* bit-exact fast path for structured matrices (Toeplitz band + one dense voiced/unvoiced state + a constant
-   * background, i.e. every matrix the reference's builders produce for S <= 384): S (2d + 2) instead of S^2 cells per
-   * frame.  Needs opts->structure from vit_analyze_structure_f32; VIT_ALGO_AUTO picks it when that says kind = 1. */
+   * background, i.e. every matrix the reference's builders produce): S (2d + 3) instead of S^2 cells per frame.  Band
+   * in registers for S <= 384, d <= 14 (dcnet / msnet / ftanet / tonet); band in tensor memory for even S <= 768,
+   * d <= 40 (jdc).  Needs opts->structure from vit_analyze_structure_f32; VIT_ALGO_AUTO picks it when that says kind = 1. */
   VIT_ALGO_BANDED = 4
 } vit_algo;
 
@@ -115,6 +116,14 @@ int vit_analyze_structure_f32(const float* h_logA_T, int S, vit_structure* out);
 /* Which algorithm VIT_ALGO_AUTO resolves to for this shape on the current device (a vit_algo), or a negative
  * vit_status. */
 int vit_select_algo(int B, int T_max, int S);
+
+/* Clips ONE launch of the chosen algorithm keeps in flight with every SM busy (persistent kernels: resident CTAs or
+ * clusters x clips per CTA; 1036 for the tensor-memory kernel at S = 361, 1184 for the banded kernels on a 148-SM B200).
+ * Hosts that split a job larger than HBM into waves (viterbi_spl_b200.waves; SURVEY.md section 8e: "choose
+ * sequences-per-CTA so every wave is full") size each wave as a multiple of it.  `structure` as in vit_decode_opts
+ * (NULL: dense kernels only).  The reference has no counterpart: it decodes one recording per call
+ * (dcnet/softmax_viterbi.py:3033-3040). */
+int vit_clips_in_flight(int S, int algo, const vit_structure* structure, int* out_clips);
 
 /* Bytes of device workspace vit_decode_f32 needs for this shape and algorithm (algo may be VIT_ALGO_AUTO).
  * The workspace holds what the reference keeps in its T1/T2 tables (imm/tf_viterbi.py:91-92): the uint16

@@ -435,3 +435,36 @@ def test_full_size_properties(Decoder):
     perm = torch.randperm(256, device=dev)
     p3, s3 = dec_c.decode_device(E[:256][perm].contiguous())
     assert torch.equal(p3, p1[:256][perm]) and torch.equal(s3, s1[:256][perm])
+
+
+# ---- jobs larger than HBM: waves (viterbi_spl_b200.waves) ----------------------------------------------------------
+
+@pytest.mark.parametrize('algo', ['auto', 'tmem'])
+def test_wave_decoder_matches_single_batch_and_oracle(Decoder, algo):
+    from viterbi_spl_b200 import _lib
+    from viterbi_spl_b200.waves import WaveDecoder, wave_bytes_per_clip
+    A, pi = hmm_params.synthetic_hmm('tonet')
+    logA_T, log_pi = hmm_params.log_params(A, pi)
+    B, T, S = 23, 50, 361
+    E = synth.batch('dense_softmax', B, T, S, seed0=300)
+    lengths = np.asarray([T - (b % 5) * 7 for b in range(B)], np.int32)
+    ref_paths, ref_scores = np_oracle.decode_batch_np(logA_T, log_pi, E, lengths)
+    dec = Decoder(logA_T, log_pi, algo=algo)
+    assert _lib.clips_in_flight(S, dec.algo, dec.structure) in (1184, 1036)      # 148 SMs x 8, 74 clusters x 14
+    dE = torch.from_numpy(E).cuda()
+    dL = torch.from_numpy(lengths).cuda()
+    wd = WaveDecoder(dec, T, budget_bytes=5 * wave_bytes_per_clip(T, S))          # 5 clips per wave -> 5 waves
+    got_p = np.full((B, T), -7, np.int64)
+    got_s = np.zeros(B, np.float32)
+
+    def fill(a, b, out):
+        out.copy_(dE[a:b])
+        return dL[a:b].contiguous()
+
+    def sink(a, b, paths, scores):
+        got_p[a:b] = paths.cpu().numpy()
+        got_s[a:b] = scores.cpu().numpy()
+
+    waves = wd.run(B, fill, sink)
+    assert [b - a for a, b in waves] == [5, 5, 5, 5, 3]
+    assert np.array_equal(got_p, ref_paths) and np.array_equal(got_s, ref_scores)

@@ -86,3 +86,23 @@ def test_voiced_and_bins():
     voiced, bins = api.voiced_and_bins(states, 320)       # dcnet/softmax_viterbi.py:2427-2431
     assert voiced.tolist() == [True, True, False, True, False]
     assert bins.tolist() == [0, 5, 319, 319, 319]
+
+
+def test_wave_planner():
+    """viterbi_spl_b200.waves.plan_waves: consecutive cover, quantum-sized waves, ragged tail only at the end."""
+    from viterbi_spl_b200.waves import plan_waves, wave_bytes_per_clip
+    per_clip = wave_bytes_per_clip(3000, 361)
+    assert per_clip == 3 * 3000 * 361 * 4 + 3000 * 8 + 4
+    # config 5 on one 180 GB B200: 65,536 clips, quantum 1036
+    waves = plan_waves(65536, per_clip, 150 * 10 ** 9, quantum=1036)
+    assert waves[0][0] == 0 and waves[-1][1] == 65536
+    assert all(a2 == b1 for (_, b1), (a2, _) in zip(waves, waves[1:]))
+    assert all((b - a) % 1036 == 0 for a, b in waves[:-1])
+    assert all((b - a) * per_clip <= 150 * 10 ** 9 for a, b in waves)
+    assert len(waves) == 6
+    # a budget below one quantum still makes progress; empty jobs give no waves; a clip larger than the budget raises
+    assert plan_waves(10, 100, 350, quantum=8) == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert plan_waves(0, 100, 1000) == []
+    assert plan_waves(5, 100, 10 ** 6, quantum=4, max_wave_clips=2) == [(0, 2), (2, 4), (4, 5)]
+    with pytest.raises(MemoryError):
+        plan_waves(3, 1000, 999)

@@ -17,7 +17,7 @@ ALGO_NAMES = {'auto': ALGO_AUTO, 'backpointer': ALGO_BACKPOINTER, 'cluster': ALG
 EXPORTS = ['vit_version', 'vit_strerror', 'vit_last_cuda_error', 'vit_launch_count', 'vit_select_algo',
            'vit_workspace_bytes', 'vit_decode_f32', 'vit_decode_f32_ex', 'vit_upload_frames_f32',
            'vit_fb_workspace_bytes', 'vit_forward_backward_f32', 'vit_emissions_f32', 'vit_voiced_bins',
-           'vit_analyze_structure_f32']
+           'vit_analyze_structure_f32', 'vit_clips_in_flight']
 
 
 class Structure(ctypes.Structure):
@@ -74,6 +74,8 @@ def load():
     L.vit_forward_backward_f32.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp, vp, vp]
     L.vit_analyze_structure_f32.restype = ci
     L.vit_analyze_structure_f32.argtypes = [vp, ci, ctypes.POINTER(Structure)]
+    L.vit_clips_in_flight.restype = ci
+    L.vit_clips_in_flight.argtypes = [ci, ci, ctypes.POINTER(Structure), ctypes.POINTER(ci)]
     L.vit_emissions_f32.restype = ci
     L.vit_emissions_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, ctypes.c_float, ci, vp, vp]
     L.vit_voiced_bins.restype = ci
@@ -96,6 +98,14 @@ def check(code):
 def workspace_bytes(B, T_max, S, algo=ALGO_AUTO):
     out = ctypes.c_size_t(0)
     check(load().vit_workspace_bytes(int(B), int(T_max), int(S), int(algo), ctypes.byref(out)))
+    return int(out.value)
+
+
+def clips_in_flight(S, algo=ALGO_AUTO, structure=None):
+    """vit_clips_in_flight: clips one launch keeps in flight with every SM busy (needs a CUDA device)."""
+    out = ctypes.c_int(0)
+    st = ctypes.byref(structure) if structure is not None else None
+    check(load().vit_clips_in_flight(int(S), int(algo), st, ctypes.byref(out)))
     return int(out.value)
 
 

@@ -46,6 +46,8 @@ int tmem_decode(const float* logA_T, const float* log_pi, const float* log_emis,
                 float* delta_out, int t_begin, int t_end, bool do_backtrace, cudaEvent_t ev0, cudaEvent_t ev1,
                 cudaStream_t stream);
 
+int tmem_clips_in_flight(int S, int* out);
+
 // vit_fb.cu
 size_t fb_workspace_bytes(int B, int T_max, int S);
 bool fb_supported(int S);
@@ -66,6 +68,7 @@ int banded_decode(const float* logA_T, const float* log_pi, const float* log_emi
                   float* scores, float* delta_out, int t_begin, int t_end, bool do_backtrace, cudaEvent_t ev0,
                   cudaEvent_t ev1, cudaStream_t stream);
 int analyze_structure(const float* A, int S, vit_structure* out);
+int banded_clips_in_flight(int* out);
 
 // vit_fb_tc.cu
 bool fb_tc_supported(int S);
@@ -128,6 +131,24 @@ int vit_select_algo(int B, int T_max, int S) {
   int rc = check_shape(B, T_max, S);
   if (rc != VIT_OK) return rc;
   return resolve_algo(VIT_ALGO_AUTO, S, false);
+}
+
+int vit_clips_in_flight(int S, int algo, const vit_structure* structure, int* out_clips) {
+  if (!out_clips) return VIT_ERR_INVALID_ARGUMENT;
+  int rc = check_shape(1, 1, S);
+  if (rc != VIT_OK) return rc;
+  if ((algo == VIT_ALGO_AUTO || algo == VIT_ALGO_BANDED) && banded_supported(S, structure))
+    return banded_clips_in_flight(out_clips);
+  if (algo == VIT_ALGO_BANDED) return VIT_ERR_UNSUPPORTED_ALGO;
+  const int a = resolve_algo(algo, S, false);
+  if (a < 0) return a;
+  if (a == VIT_ALGO_TMEM) return tmem_clips_in_flight(S, out_clips);
+  // cluster / backpointer kernels: no fixed quantum worth planning for; one clip per SM is the natural unit
+  int num_sms = 148, dev = 0;
+  VIT_CUDA_TRY(cudaGetDevice(&dev));
+  VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  *out_clips = num_sms;
+  return VIT_OK;
 }
 
 int vit_workspace_bytes(int B, int T_max, int S, int algo, size_t* out_bytes) {

@@ -55,6 +55,13 @@ __device__ __forceinline__ float warp_max_f(float v) {
   return v;
 }
 
+// one-instruction warp maximum (sm_100a: CREDUX.MAX.F32; NaNs are ignored, +0 / -0 compare equal downstream)
+__device__ __forceinline__ float warp_max_redux(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 template <int D>
 __global__ void __launch_bounds__(bThreads, 1)
 banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict__ log_pi,
@@ -77,27 +84,26 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
   // ---- one-time: my band entries -> registers; dense-column and dense-row entries --------------------------------
   // a[n][r] = logA^T[j0+n][j0+n + r - D]; entries that fall outside the matrix, on the dense state's row or on the
   // dense state's column are -inf (the dense column has its own term, the dense row its own code)
-  float a[bNJ][W], acol[bNJ], arow[4];
+  float a[bNJ][W], acol[bNJ], arow[bNJ];
+  bool jn_ok[bNJ];
 #pragma unroll
   for (int n = 0; n < bNJ; ++n) {
     const int j = j0 + n;
     const bool jok = j < S && j != jd;
+    jn_ok[n] = jok;
 #pragma unroll
     for (int r = 0; r < W; ++r) {
       const int i = j + r - D;
       a[n][r] = (jok && i >= 0 && i < S && i != jd) ? logA_T[(size_t)j * S + i] : -INFINITY;
     }
-    acol[n] = (jok && jd >= 0) ? logA_T[(size_t)j * S + jd] : -INFINITY;
+    acol[n] = (jok && jd >= 0) ? logA_T[(size_t)j * S + jd] : -INFINITY;   // dense source column: A[jd -> j]
+    arow[n] = (jok && jd >= 0) ? logA_T[(size_t)jd * S + j] : -INFINITY;   // dense target row:    A[j -> jd]
   }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int i = tgw * 128 + lane + 32 * k;
-    arow[k] = (jd >= 0 && i < S) ? logA_T[(size_t)jd * S + i] : -INFINITY;
-  }
-  bool jn_ok[bNJ];
-#pragma unroll
-  for (int n = 0; n < bNJ; ++n) jn_ok[n] = (j0 + n) < S && (j0 + n) != jd;
+  const float a_dd = jd >= 0 ? logA_T[(size_t)jd * S + jd] : -INFINITY;
+  // a warp whose 128 targets are all band states takes the unpredicated loads / stores
+  const bool wfull = __all_sync(0xffffffffu, jn_ok[0] && jn_ok[1] && jn_ok[2] && jn_ok[3]);
   const long long hist_delta = reinterpret_cast<const char*>(hist) - reinterpret_cast<const char*>(log_emis);
+  const int jd_off = jd - j0;                                // logE[..][jd] relative to my emission pointer
 
   for (int seq0 = blockIdx.x * bMB; seq0 < B; seq0 += gridDim.x * bMB) {
     __syncthreads();
@@ -115,84 +121,79 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
     int maxlen = 0;
 #pragma unroll
     for (int c = 0; c < bCPT; ++c) maxlen = max(maxlen, len[c]);
-    // address of logE[clip][t][j0], advanced one frame per step; the history sits at a fixed distance
+    // address of logE[clip][t][j0], advanced one frame per step; the history sits at a fixed distance.  A clip keeps
+    // stepping (on whatever its rows hold) until the longest clip of its pipeline is done -- nothing of it is stored
+    // past its length -- and a slot past the batch aliases the last clip's rows, so no load needs a per-step predicate.
     const float* pe[bCPT];
 #pragma unroll
-    for (int c = 0; c < bCPT; ++c) pe[c] = log_emis + ((size_t)(seq0 + c0 + c) * T_max + t_begin) * S + j0;
-    const int jd_off = jd - j0;                              // logE[..][jd] relative to pe[c]
+    for (int c = 0; c < bCPT; ++c) pe[c] = log_emis + ((size_t)min(seq0 + c0 + c, B - 1) * T_max + t_begin) * S + j0;
     const int t_stop = min(maxlen, t_end);
+    float xd[bCPT];                                          // delta_{t-1}[jd] of my clips
+#pragma unroll
+    for (int c = 0; c < bCPT; ++c) xd[c] = -INFINITY;
     if (t_begin > 0 && t_begin < t_stop) {
-      // resume a frame range: delta_{t_begin-1} comes back from the history -- my 4 targets into the delta row, their
-      // maximum and the dense state's value into the per-warp partials the first step will combine
+      // resume a frame range: delta_{t_begin-1} comes back from the history -- my 4 targets into the delta row, the
+      // per-warp partials the first step will combine, and the dense state's own value
       const int pb = (t_begin - 1) & 1;
 #pragma unroll
       for (int c = 0; c < bCPT; ++c) {
-        const float* row = hist + ((size_t)(seq0 + c0 + c) * T_max + (t_begin - 1)) * S;
-        const bool lv = t_begin - 1 < len[c];
-        float v[bNJ], mloc = -INFINITY;
+        const float* row = reinterpret_cast<const float*>(reinterpret_cast<const char*>(pe[c]) + hist_delta) - S - j0;
+        float v[bNJ], mloc = -INFINITY, dloc = -INFINITY;
 #pragma unroll
         for (int n = 0; n < bNJ; ++n) {
-          v[n] = (lv && jn_ok[n]) ? row[j0 + n] : -INFINITY;
+          v[n] = jn_ok[n] ? row[j0 + n] : -INFINITY;
           mloc = fmaxf(mloc, v[n]);
+          dloc = fmaxf(dloc, __fadd_rn(v[n], arow[n]));
         }
         reinterpret_cast<float4*>(s_delta[cs][pb][c] + DP)[tg] = make_float4(v[0], v[1], v[2], v[3]);
-        mloc = warp_max_f(mloc);
+        mloc = warp_max_redux(mloc);
+        dloc = warp_max_redux(dloc);
         if (lane == 0) {
           s_partM[cs][pb][tgw][c] = mloc;
-          s_partD[cs][pb][tgw][c] = (lv && jd >= 0) ? row[jd] : -INFINITY;      // + ed_prev (= 0) gives delta[jd] back
+          s_partD[cs][pb][tgw][c] = dloc;
         }
+        xd[c] = jd >= 0 ? row[jd] : -INFINITY;
       }
       bpipe_bar_sync(cs);
     }
 
-    float ed_prev[bCPT];                                     // logE[t-1][jd] of my clips
-#pragma unroll
-    for (int c = 0; c < bCPT; ++c) ed_prev[c] = 0.f;
     for (int t = t_begin; t < t_stop; ++t) {
       const int buf = t & 1;
       // keep the two running pointers in registers (ptxas would otherwise re-derive the 64-bit address of every load)
 #pragma unroll
       for (int c = 0; c < bCPT; ++c) asm volatile("" : "+l"(pe[c]));
-      bool live[bCPT];
-#pragma unroll
-      for (int c = 0; c < bCPT; ++c) live[c] = t < len[c];
-      // this step's emissions: issued first, used last.  The dense state's emission is fetched by one lane per warp.
+      // this step's emissions: issued first, used last
       float e[bCPT][bNJ], ed[bCPT];
+      const bool pf = (lane & 7) == 0 && t + 4 < T_max;
 #pragma unroll
       for (int c = 0; c < bCPT; ++c) {
         // a step is shorter than an HBM round trip: pull the lines of frame t + 4 into L2 now (one lane per 128 B)
-        if ((lane & 7) == 0 && t + 4 < len[c]) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe[c] + 4 * (size_t)S));
+        if (pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe[c] + 4 * (size_t)S));
+        if (wfull) {
 #pragma unroll
-        for (int n = 0; n < bNJ; ++n) e[c][n] = (live[c] && jn_ok[n]) ? __ldg(pe[c] + n) : 0.f;
-        ed[c] = (lane == 0 && live[c] && jd >= 0) ? __ldg(pe[c] + jd_off) : 0.f;
+          for (int n = 0; n < bNJ; ++n) e[c][n] = __ldg(pe[c] + n);
+        } else {
+#pragma unroll
+          for (int n = 0; n < bNJ; ++n) e[c][n] = jn_ok[n] ? __ldg(pe[c] + n) : 0.f;
+        }
+        ed[c] = jd >= 0 ? __ldg(pe[c] + jd_off) : 0.f;      // one address per warp
       }
 
-      float acc[bCPT][bNJ], pd[bCPT], xd[bCPT];
+      float acc[bCPT][bNJ], xdn[bCPT];
       if (t == 0) {
         // T1[0] = log_pi + logE[0]                                                              (imm/tf_viterbi.py:94)
 #pragma unroll
         for (int c = 0; c < bCPT; ++c) {
 #pragma unroll
           for (int n = 0; n < bNJ; ++n) acc[c][n] = jn_ok[n] ? log_pi[j0 + n] : -INFINITY;
-          pd[c] = jd >= 0 ? log_pi[jd] : -INFINITY;
-          xd[c] = -INFINITY;
+          xdn[c] = jd >= 0 ? __fadd_rn(log_pi[jd], ed[c]) : -INFINITY;
         }
       } else {
 #pragma unroll
         for (int c = 0; c < bCPT; ++c) {
           const float* prev = s_delta[cs][buf ^ 1][c];
-          // combine the per-warp partials of step t-1: delta_{t-1}[jd] and max_i delta_{t-1}[i]
-          const float* pm = &s_partM[cs][buf ^ 1][0][c];
-          const float* pdd = &s_partD[cs][buf ^ 1][0][c];
-          float dm = fmaxf(fmaxf(pm[0], pm[bCPT]), pm[2 * bCPT]);
-          xd[c] = (jd >= 0) ? __fadd_rn(fmaxf(fmaxf(pdd[0], pdd[bCPT]), pdd[2 * bCPT]), ed_prev[c]) : -INFINITY;
-          dm = fmaxf(dm, xd[c]);
-          if (jd >= 0 && tgw == 0 && lane == 0 && t - 1 < len[c] && t - 1 >= t_begin)
-            st_global_cs_f32(hist + ((size_t)(seq0 + c0 + c) * T_max + (t - 1)) * S + jd, xd[c]);
-          // background term fl(max_i delta_i + c) and the dense source column
-          const float bg = __fadd_rn(dm, cbg);
 #pragma unroll
-          for (int n = 0; n < bNJ; ++n) acc[c][n] = fmaxf(bg, __fadd_rn(xd[c], acol[n]));
+          for (int n = 0; n < bNJ; ++n) acc[c][n] = -INFINITY;
           // the band: my window of delta_{t-1} is NW4 aligned float4s starting at my own targets' slot.  One float4 at
           // a time, applied to every (offset r, target n) cell that reads it: only 4 window values are ever live
           const float4* row4 = reinterpret_cast<const float4*>(prev) + tg;
@@ -208,63 +209,59 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
                 if (r >= 0 && r < W) acc[c][n] = fmaxf(acc[c][n], __fadd_rn(wv[k], a[n][r]));
               }
           }
-          // my share of the dense target row: sources tgw*128 + lane + 32 k
-          float m = -INFINITY;
+          // combine the per-warp partials of step t-1: max_{i != jd} delta_{t-1}[i] and the dense target row's
+          // max_{i != jd} fl(delta_{t-1}[i] + A[i -> jd]); then delta_t[jd], the background term fl(max_i delta_i + c)
+          // and the dense source column
+          const float* pm = &s_partM[cs][buf ^ 1][0][c];
+          const float* pdd = &s_partD[cs][buf ^ 1][0][c];
+          const float dm = fmaxf(fmaxf(fmaxf(pm[0], pm[bCPT]), pm[2 * bCPT]), xd[c]);
+          const float dd = fmaxf(fmaxf(fmaxf(pdd[0], pdd[bCPT]), pdd[2 * bCPT]), __fadd_rn(xd[c], a_dd));
+          xdn[c] = jd >= 0 ? __fadd_rn(dd, ed[c]) : -INFINITY;
+          const float bg = __fadd_rn(dm, cbg);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int i = tgw * 128 + lane + 32 * k;
-            float dv = (i < S) ? prev[i + DP] : -INFINITY;
-            if (i == jd) dv = xd[c];
-            m = fmaxf(m, __fadd_rn(dv, arow[k]));
-          }
-          pd[c] = m;
+          for (int n = 0; n < bNJ; ++n) acc[c][n] = fmaxf(acc[c][n], fmaxf(bg, __fadd_rn(xd[c], acol[n])));
         }
       }
 
       // T1[t][j] = max + logE[t][j]                                                              (:100)
-      float pm[bCPT];
 #pragma unroll
       for (int c = 0; c < bCPT; ++c) {
         float v[bNJ];
-        float mloc = -INFINITY;
+        float mloc = -INFINITY, dloc = -INFINITY;
+        float* ph = reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<float*>(pe[c])) + hist_delta);
+        const bool st = t < len[c];
+        if (wfull) {
+#pragma unroll
+          for (int n = 0; n < bNJ; ++n) {
+            v[n] = __fadd_rn(acc[c][n], e[c][n]);
+            if (st) st_global_cs_f32(ph + n, v[n]);
+          }
+        } else {
+#pragma unroll
+          for (int n = 0; n < bNJ; ++n) {
+            v[n] = jn_ok[n] ? __fadd_rn(acc[c][n], e[c][n]) : -INFINITY;
+            if (st && jn_ok[n]) st_global_cs_f32(ph + n, v[n]);
+          }
+        }
 #pragma unroll
         for (int n = 0; n < bNJ; ++n) {
-          v[n] = jn_ok[n] ? __fadd_rn(acc[c][n], e[c][n]) : -INFINITY;
-          if (live[c] && jn_ok[n])
-            st_global_cs_f32(reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<float*>(pe[c])) + hist_delta) + n, v[n]);
           mloc = fmaxf(mloc, v[n]);
+          dloc = fmaxf(dloc, __fadd_rn(v[n], arow[n]));
         }
         // one aligned float4 (slots of non-existent / dense targets get -inf, which is what they must hold)
         reinterpret_cast<float4*>(s_delta[cs][buf][c] + DP)[tg] = make_float4(v[0], v[1], v[2], v[3]);
-        pm[c] = warp_max_f(mloc);
-        pd[c] = warp_max_f(pd[c]);
-        ed[c] = __shfl_sync(0xffffffffu, ed[c], 0);
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int c = 0; c < bCPT; ++c) {
-          s_partM[cs][buf][tgw][c] = pm[c];
-          s_partD[cs][buf][tgw][c] = pd[c];
+        mloc = warp_max_redux(mloc);
+        dloc = warp_max_redux(dloc);
+        if (lane == 0) {
+          s_partM[cs][buf][tgw][c] = mloc;
+          s_partD[cs][buf][tgw][c] = dloc;
         }
-      }
-#pragma unroll
-      for (int c = 0; c < bCPT; ++c) {
-        ed_prev[c] = ed[c];
+        // the dense state's own value of this frame (every thread has it; one stores it)
+        if (jd >= 0 && tgw == 0 && lane == 1 && st) st_global_cs_f32(ph + jd_off, xdn[c]);
+        xd[c] = xdn[c];
         pe[c] += S;
       }
       bpipe_bar_sync(cs);
-    }
-    // the dense state's value of the last frame
-    if (jd >= 0 && t_stop > t_begin && tgw == 0 && lane == 0) {
-      const int buf = (t_stop - 1) & 1;
-#pragma unroll
-      for (int c = 0; c < bCPT; ++c) {
-        if (t_stop - 1 < len[c]) {
-          const float* pdd = &s_partD[cs][buf][0][c];
-          const float x = __fadd_rn(fmaxf(fmaxf(pdd[0], pdd[bCPT]), pdd[2 * bCPT]), ed_prev[c]);
-          st_global_cs_f32(hist + ((size_t)(seq0 + c0 + c) * T_max + (t_stop - 1)) * S + jd, x);
-        }
-      }
     }
   }
 }
@@ -296,6 +293,16 @@ static bool banded_narrow_supported(int S, const vit_structure* st) {
 bool banded_supported(int S, const vit_structure* st) {
   if (!st || st->kind != 1) return false;
   return banded_narrow_supported(S, st) || banded_wide_supported(S, st);
+}
+
+// both banded kernels: one CTA per SM, 8 clips per CTA
+int banded_clips_in_flight(int* out) {
+  static_assert(bMB == 8, "vit_banded_wide.cu keeps 8 clips per CTA as well");
+  int num_sms = 148, dev = 0;
+  VIT_CUDA_TRY(cudaGetDevice(&dev));
+  VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  *out = num_sms * bMB;
+  return VIT_OK;
 }
 
 size_t banded_workspace_bytes(int B, int T_max, int S) {

@@ -310,6 +310,63 @@ static auto pick_kernel(int KP) -> decltype(&tmem_forward_kernel<NJ, 0>) {
   return tmem_forward_kernel<NJ, 0>;
 }
 
+using TmemKernel = decltype(&tmem_forward_kernel<1, 0>);
+
+// kernel instance, launch configuration (cluster attribute in attr[0]) and the number of clusters that can be
+// co-resident for a plan: TMEM is allocated whole, so one CTA per SM
+static int tmem_geometry(const TmemPlan& p, TmemKernel* kern_out, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr,
+                         int* max_clusters_out) {
+  TmemKernel kern = nullptr;
+  switch (p.NJ) {
+    case 1: kern = pick_kernel<1>(p.KP); break;
+    case 2: kern = pick_kernel<2>(p.KP); break;
+    case 3: kern = pick_kernel<3>(p.KP); break;
+    case 4: kern = pick_kernel<4>(p.KP); break;
+    case 5: kern = pick_kernel<5>(p.KP); break;
+    case 6: kern = pick_kernel<6>(p.KP); break;
+    default: return VIT_ERR_UNSUPPORTED_ALGO;
+  }
+  // at least 120 KB so that two CTAs can never share an SM: each allocates all 512 TMEM columns, and a CTA waiting
+  // for its peer's columns while that peer's cluster waits for ours would deadlock
+  size_t smem = tmem_smem_bytes(p);
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  VIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cfg->blockDim = dim3(tThreads);
+  cfg->dynamicSmemBytes = smem;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg->attrs = attr;
+  cfg->numAttrs = 1;
+  // persistent grid: as many clusters as can be co-resident (TMEM is allocated whole, so 1 CTA per SM)
+  int max_clusters = 0;
+  cfg->gridDim = dim3(p.C);
+  VIT_CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, kern, cfg));
+  if (max_clusters < 1) return VIT_ERR_UNSUPPORTED_ALGO;
+  int num_sms = 148, devid = 0;
+  VIT_CUDA_TRY(cudaGetDevice(&devid));
+  VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, devid));
+  if (max_clusters * p.C > num_sms) max_clusters = num_sms / p.C;   // one CTA per SM: TMEM is not shareable here
+  *kern_out = kern;
+  *max_clusters_out = max_clusters;
+  return VIT_OK;
+}
+
+// clips one launch keeps in flight with every cluster busy (the wave quantum of viterbi_spl_b200.waves)
+int tmem_clips_in_flight(int S, int* out) {
+  TmemPlan p;
+  if (!make_tmem_plan(S, &p)) return VIT_ERR_UNSUPPORTED_ALGO;
+  TmemKernel kern = nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  int max_clusters = 0;
+  const int rc = tmem_geometry(p, &kern, &cfg, attr, &max_clusters);
+  if (rc != VIT_OK) return rc;
+  *out = max_clusters * tPipes * tMB;
+  return VIT_OK;
+}
+
 int tmem_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths,
                 int B, int T_max, int S, void* workspace, size_t workspace_bytes,
                 int64_t* paths, float* scores, float* delta_out, int t_begin, int t_end, bool do_backtrace,
@@ -337,43 +394,13 @@ int tmem_decode(const float* logA_T, const float* log_pi, const float* log_emis,
     }
     const char* dev_s = getenv("VIT_DEV_FLAGS");
     const int dev = dev_s ? atoi(dev_s) : 0;
-    decltype(&tmem_forward_kernel<1, 0>) kern = nullptr;
-    switch (p.NJ) {
-      case 1: kern = pick_kernel<1>(p.KP); break;
-      case 2: kern = pick_kernel<2>(p.KP); break;
-      case 3: kern = pick_kernel<3>(p.KP); break;
-      case 4: kern = pick_kernel<4>(p.KP); break;
-      case 5: kern = pick_kernel<5>(p.KP); break;
-      case 6: kern = pick_kernel<6>(p.KP); break;
-      default: return VIT_ERR_UNSUPPORTED_ALGO;
-    }
-    // at least 120 KB so that two CTAs can never share an SM: each allocates all 512 TMEM columns, and a CTA waiting
-    // for its peer's columns while that peer's cluster waits for ours would deadlock
-    size_t smem = tmem_smem_bytes(p);
-    if (smem < 120 * 1024) smem = 120 * 1024;
-    VIT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-
+    TmemKernel kern = nullptr;
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(tThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = p.C;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    // persistent grid: as many clusters as can be co-resident (TMEM is allocated whole, so 1 CTA per SM), but no
-    // more than there are sub-batches
     int max_clusters = 0;
-    cfg.gridDim = dim3(p.C);
-    VIT_CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
-    if (max_clusters < 1) return VIT_ERR_UNSUPPORTED_ALGO;
-    int num_sms = 148, devid = 0;
-    VIT_CUDA_TRY(cudaGetDevice(&devid));
-    VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, devid));
-    if (max_clusters * p.C > num_sms) max_clusters = num_sms / p.C;   // one CTA per SM: TMEM is not shareable here
+    const int grc = tmem_geometry(p, &kern, &cfg, attr, &max_clusters);
+    if (grc != VIT_OK) return grc;
+    cfg.stream = stream;
     const int sub_batches = (B + tMB - 1) / tMB;                      // one per pipeline
     const int want = (sub_batches + tPipes - 1) / tPipes;
     const int n_clusters = want < max_clusters ? want : max_clusters;
