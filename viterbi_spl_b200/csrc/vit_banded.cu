@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "vit_common.cuh"
@@ -66,7 +67,10 @@ template <int D>
 __global__ void __launch_bounds__(bThreads, 1)
 banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict__ log_pi,
                       const float* __restrict__ log_emis, const int32_t* __restrict__ lengths, int B, int T_max, int S,
-                      int jd, float cbg, float* __restrict__ hist, int t_begin, int t_end) {
+                      int jd, float cbg, float* __restrict__ hist, int t_begin, int t_end, int q) {
+  // q: clips per CTA and pass (1..8).  The host spreads a batch evenly (1024 clips = 147 CTAs x 7, not 128 x 8): pipeline
+  // cs takes clips [2 cs, 2 cs + 2) of the CTA's q, so the last busy pipeline may hold ONE clip and then runs the
+  // one-clip instance of the step (half the cells), and a pipeline past q sits the pass out.
   constexpr int W = 2 * D + 1;
   constexpr int DP = (D + 3) / 4 * 4;
   constexpr int U0 = DP - D;                         // window element of cell (r, n) = w[U0 + r + n]
@@ -105,38 +109,33 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
   const long long hist_delta = reinterpret_cast<const char*>(hist) - reinterpret_cast<const char*>(log_emis);
   const int jd_off = jd - j0;                                // logE[..][jd] relative to my emission pointer
 
-  for (int seq0 = blockIdx.x * bMB; seq0 < B; seq0 += gridDim.x * bMB) {
-    __syncthreads();
-    if (tid < bMB) {
-      const int b = seq0 + tid;
-      s_len[tid] = b < B ? (lengths ? lengths[b] : T_max) : 0;
-    }
-    // (re-)arm the delta rows: pads, out-of-range states and the dense state's slot stay -inf for the whole sub-batch
-    for (int x = tid; x < bCS * 2 * bCPT * bRowLen; x += bThreads) (&s_delta[0][0][0][0])[x] = -INFINITY;
-    __syncthreads();
-    const int c0 = cs * bCPT;
-    int len[bCPT];
+  const int c0 = cs * bCPT;
+  const int ncl = min(bCPT, q - c0);                         // clips of this pipeline (<= 0: idle)
+  // the body of one pass, instantiated for 2 and for 1 clips per thread
+  auto run_pass = [&](auto cpt_tag, int seq0) {
+    constexpr int CPT = decltype(cpt_tag)::value;
+    int len[CPT];
 #pragma unroll
-    for (int c = 0; c < bCPT; ++c) len[c] = s_len[c0 + c];
+    for (int c = 0; c < CPT; ++c) len[c] = s_len[c0 + c];
     int maxlen = 0;
 #pragma unroll
-    for (int c = 0; c < bCPT; ++c) maxlen = max(maxlen, len[c]);
+    for (int c = 0; c < CPT; ++c) maxlen = max(maxlen, len[c]);
     // address of logE[clip][t][j0], advanced one frame per step; the history sits at a fixed distance.  A clip keeps
     // stepping (on whatever its rows hold) until the longest clip of its pipeline is done -- nothing of it is stored
     // past its length -- and a slot past the batch aliases the last clip's rows, so no load needs a per-step predicate.
-    const float* pe[bCPT];
+    const float* pe[CPT];
 #pragma unroll
-    for (int c = 0; c < bCPT; ++c) pe[c] = log_emis + ((size_t)min(seq0 + c0 + c, B - 1) * T_max + t_begin) * S + j0;
+    for (int c = 0; c < CPT; ++c) pe[c] = log_emis + ((size_t)min(seq0 + c0 + c, B - 1) * T_max + t_begin) * S + j0;
     const int t_stop = min(maxlen, t_end);
-    float xd[bCPT];                                          // delta_{t-1}[jd] of my clips
+    float xd[CPT];                                          // delta_{t-1}[jd] of my clips
 #pragma unroll
-    for (int c = 0; c < bCPT; ++c) xd[c] = -INFINITY;
+    for (int c = 0; c < CPT; ++c) xd[c] = -INFINITY;
     if (t_begin > 0 && t_begin < t_stop) {
       // resume a frame range: delta_{t_begin-1} comes back from the history -- my 4 targets into the delta row, the
       // per-warp partials the first step will combine, and the dense state's own value
       const int pb = (t_begin - 1) & 1;
 #pragma unroll
-      for (int c = 0; c < bCPT; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         const float* row = reinterpret_cast<const float*>(reinterpret_cast<const char*>(pe[c]) + hist_delta) - S - j0;
         float v[bNJ], mloc = -INFINITY, dloc = -INFINITY;
 #pragma unroll
@@ -161,12 +160,12 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
       const int buf = t & 1;
       // keep the two running pointers in registers (ptxas would otherwise re-derive the 64-bit address of every load)
 #pragma unroll
-      for (int c = 0; c < bCPT; ++c) asm volatile("" : "+l"(pe[c]));
+      for (int c = 0; c < CPT; ++c) asm volatile("" : "+l"(pe[c]));
       // this step's emissions: issued first, used last
-      float e[bCPT][bNJ], ed[bCPT];
+      float e[CPT][bNJ], ed[CPT];
       const bool pf = (lane & 7) == 0 && t + 4 < T_max;
 #pragma unroll
-      for (int c = 0; c < bCPT; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         // a step is shorter than an HBM round trip: pull the lines of frame t + 4 into L2 now (one lane per 128 B)
         if (pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe[c] + 4 * (size_t)S));
         if (wfull) {
@@ -179,18 +178,18 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
         ed[c] = jd >= 0 ? __ldg(pe[c] + jd_off) : 0.f;      // one address per warp
       }
 
-      float acc[bCPT][bNJ], xdn[bCPT];
+      float acc[CPT][bNJ], xdn[CPT];
       if (t == 0) {
         // T1[0] = log_pi + logE[0]                                                              (imm/tf_viterbi.py:94)
 #pragma unroll
-        for (int c = 0; c < bCPT; ++c) {
+        for (int c = 0; c < CPT; ++c) {
 #pragma unroll
           for (int n = 0; n < bNJ; ++n) acc[c][n] = jn_ok[n] ? log_pi[j0 + n] : -INFINITY;
           xdn[c] = jd >= 0 ? __fadd_rn(log_pi[jd], ed[c]) : -INFINITY;
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < bCPT; ++c) {
+        for (int c = 0; c < CPT; ++c) {
           const float* prev = s_delta[cs][buf ^ 1][c];
 #pragma unroll
           for (int n = 0; n < bNJ; ++n) acc[c][n] = -INFINITY;
@@ -225,7 +224,7 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
 
       // T1[t][j] = max + logE[t][j]                                                              (:100)
 #pragma unroll
-      for (int c = 0; c < bCPT; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         float v[bNJ];
         float mloc = -INFINITY, dloc = -INFINITY;
         float* ph = reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<float*>(pe[c])) + hist_delta);
@@ -263,6 +262,19 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
       }
       bpipe_bar_sync(cs);
     }
+  };
+
+  for (int seq0 = blockIdx.x * q; seq0 < B; seq0 += gridDim.x * q) {
+    __syncthreads();
+    if (tid < bMB) {
+      const int b = seq0 + tid;
+      s_len[tid] = (tid < q && b < B) ? (lengths ? lengths[b] : T_max) : 0;
+    }
+    // (re-)arm the delta rows: pads, out-of-range states and the dense state's slot stay -inf for the whole sub-batch
+    for (int x = tid; x < bCS * 2 * bCPT * bRowLen; x += bThreads) (&s_delta[0][0][0][0])[x] = -INFINITY;
+    __syncthreads();
+    if (ncl >= 2) run_pass(std::integral_constant<int, 2>{}, seq0);
+    else if (ncl == 1) run_pass(std::integral_constant<int, 1>{}, seq0);
   }
 }
 
@@ -334,14 +346,18 @@ int banded_decode(const float* logA_T, const float* log_pi, const float* log_emi
   int num_sms = 148, dev = 0;
   VIT_CUDA_TRY(cudaGetDevice(&dev));
   VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  const int want = (B + bMB - 1) / bMB;
+  // spread the clips evenly over the SMs: `passes` trips of q <= 8 clips per CTA (1024 clips: 147 CTAs x 7)
+  const int passes = (B + bMB * num_sms - 1) / (bMB * num_sms);
+  int q = (B + passes * num_sms - 1) / (passes * num_sms);
+  q = q < 1 ? 1 : (q > bMB ? bMB : q);
+  const int want = (B + q - 1) / q;
   const int grid = want < num_sms ? want : num_sms;
   if (ev0) VIT_CUDA_TRY(cudaEventRecord(ev0, stream));
 #define VIT_BANDED_CASE(DD)                                                                                          \
   case DD: {                                                                                                         \
     banded_forward_kernel<DD><<<grid, bThreads, 0, stream>>>(logA_T, log_pi, log_emis, lengths, B, T_max, S,         \
                                                               st->dense_index, st->background, hist, t_begin,       \
-                                                              t_end);                                                \
+                                                              t_end, q);                                             \
   } break;
   switch (D) {
     VIT_BANDED_CASE(4) VIT_BANDED_CASE(8) VIT_BANDED_CASE(12) VIT_BANDED_CASE(14)
