@@ -194,6 +194,28 @@ int vit_emissions_f32(const float* d_logits, const float* d_prior, int B, int T,
 int vit_voiced_bins(const int64_t* d_states, long long n, int n_bins, uint8_t* d_voiced, int64_t* d_bins, void* stream);
 
 /*
+ * The statistics step after the decode, batched (MetricsInference.viterbi_update_states_tf_fn,
+ * dcnet/softmax_viterbi.py:2923-2979, with est_notes_fn, dcnet/main.py:1911-1934): per frame the decoded bin and its
+ * two neighbours, weighted by sigmoid(logit), give the refined note
+ *     note = sum_{|k-bin|<=1} (k * note_step) p_k / max(sum p_k, 1e-3) + note_min        (note_min 23.6, step 1/5)
+ * and nine int64 counters per clip, in the reference's order: reference voiced, reference unvoiced, correct voiced,
+ * incorrect voiced, correct unvoiced, pitch hits wide, strict, chroma hits wide, strict.
+ *   d_logits   [B][T][logit_stride] float32; bin k of a frame is element logit_offset + k (offset 0 / stride n_bins
+ *              for the dcnet form, offset 1 / stride n_bins + 1 where column 0 is the unvoiced logit)
+ *   d_ref_notes[B][T] float32 (<= 0.1: unvoiced, :2938);  d_bins / d_voiced: what vit_voiced_bins produced
+ *   d_lengths  [B] or NULL;  frames past a clip's length count nowhere and get est_note 0
+ *   d_est_notes[B][T] out: +note where decoded voiced, -note where not (:2975)
+ *   d_counters [B][VIT_MELODY_COUNTERS] int64 out (zeroed by the call)
+ * The reference's version is TensorFlow (absent from this image): float32 like it, checked against a NumPy
+ * restatement (oracle/post_oracle.py) to 1e-5 on notes -- parity unpinned for this entry point.
+ */
+#define VIT_MELODY_COUNTERS 9
+int vit_melody_stats_f32(const float* d_logits, int logit_stride, int logit_offset, const float* d_ref_notes,
+                         const int64_t* d_bins, const uint8_t* d_voiced, const int32_t* d_lengths, int B, int T,
+                         int n_bins, float note_min, float note_step, float* d_est_notes, int64_t* d_counters,
+                         void* stream);
+
+/*
  * Host -> device upload of frames [frame_begin, frame_end) of every clip of a [B][T_max][S] float32 batch: one strided
  * 2-D async copy on `stream` (h_log_emis should be page-locked for the copy to be asynchronous).  Together with the
  * frame ranges of vit_decode_f32_ex this lets a host overlap the PCIe transfer of time slab k+1 with the recursion

@@ -85,3 +85,68 @@ def test_voiced_bins_and_batched_pipeline(pl):
     assert np.array_equal(voiced.cpu().numpy(), (st >= 0) & (st < 360))
     assert np.array_equal(bins.cpu().numpy(), np.where(st < 0, -1, np.minimum(st, 359)))
     assert not voiced[1].any() and (bins[1] == -1).all()
+
+
+# ---- post-decode statistics (vit_melody_stats_f32) vs the NumPy restatement of the reference's TF step -------------
+
+def _stats_case(seed, T, n_bins=320):
+    rng = np.random.default_rng(seed)
+    logits = rng.normal(0, 3, (T, n_bins)).astype(np.float32)
+    bins = rng.integers(0, n_bins, T)
+    bins[:4] = np.asarray((0, n_bins - 1, 1, n_bins - 2))[:T]                                  # window clipped at both ends of the bin range
+    voiced = rng.random(T) < 0.6
+    ref = (23.6 + bins / 5. + rng.normal(0, 0.4, T)).astype(np.float32)        # around the decoded bin: hits and misses
+    ref[rng.random(T) < 0.15] += 12.                                           # octave errors: chroma hit, pitch miss
+    ref[rng.random(T) < 0.3] = 0.                                              # unvoiced reference frames
+    return logits, ref, bins, voiced
+
+
+def test_melody_stats_match_the_reference_restatement(pl):
+    from oracle import post_oracle
+    cases = [_stats_case(s, T) for s, T in ((1, 700), (2, 1), (3, 257), (4, 1200))]
+    T_max = max(c[0].shape[0] for c in cases)
+    B = len(cases)
+    L = np.zeros((B, T_max, 320), np.float32)
+    R = np.zeros((B, T_max), np.float32)
+    Bn = np.full((B, T_max), -1, np.int64)
+    V = np.zeros((B, T_max), bool)
+    lengths = np.asarray([c[0].shape[0] for c in cases], np.int32)
+    for b, (lg, ref, bins, voiced) in enumerate(cases):
+        n = len(ref)
+        L[b, :n], R[b, :n], Bn[b, :n], V[b, :n] = lg, ref, bins, voiced
+    est, counters = pl.melody_stats_device(torch.as_tensor(L).cuda(), torch.as_tensor(R), torch.as_tensor(Bn),
+                                           torch.as_tensor(V), lengths)
+    est, counters = est.cpu().numpy(), counters.cpu().numpy()
+    for b, (lg, ref, bins, voiced) in enumerate(cases):
+        n = len(ref)
+        want, c = post_oracle.melody_stats_np(ref, lg, bins, voiced)
+        assert np.allclose(est[b, :n], want, rtol=1e-5, atol=1e-5), np.abs(est[b, :n] - want).max()
+        assert np.all(est[b, n:] == 0)
+        got = dict(zip(pl.COUNTER_NAMES, counters[b].tolist()))
+        assert pl.COUNTER_NAMES == post_oracle.COUNTERS
+        # a note within 1e-5 of a 0.5 threshold may fall on either side: allow that many frames of slack per counter
+        diff = np.abs(np.abs(want) - ref)
+        edge = int(np.sum(np.abs(diff - 0.5) < 2e-5) + np.sum(np.abs(np.abs(diff - np.round(diff / 12) * 12) - 0.5) < 2e-5))
+        for k in pl.COUNTER_NAMES:
+            assert abs(got[k] - c[k]) <= edge, (b, k, got[k], c[k])
+        for k in pl.COUNTER_NAMES[:5]:
+            assert got[k] == c[k], (b, k)
+        assert got['gt_voiced'] + got['gt_unvoiced'] == n
+
+
+def test_melody_stats_softmax_layout_and_pipeline_evaluate(pl):
+    """Column 0 = unvoiced logit (offset 1), through MelodyPipeline.evaluate on the shipped msnet parameters."""
+    from oracle import post_oracle
+    ml = np.load(os.path.join(GOLD, 'msnet_logdomain.npz'))
+    m = np.load(os.path.join(GOLD, 'msnet_softmax_viterbi.npz'))
+    A = np.exp(ml['logA_T'].T.astype(np.float64)).astype(np.float32)
+    mp = pl.MelodyPipeline(A, ml['ini_probs'], model='softmax', scaled=False)
+    logits = m['logits']                                                        # [T, 321]
+    T = logits.shape[0]
+    rng = np.random.default_rng(5)
+    ref = np.where(rng.random(T) < 0.5, 23.6 + rng.integers(0, 320, T) / 5., 0.).astype(np.float32)
+    voiced, bins, est, counters = mp.evaluate(logits[None], ref[None])
+    want, c = post_oracle.melody_stats_np(ref, logits[:, 1:], bins[0].cpu().numpy(), voiced[0].cpu().numpy())
+    assert np.allclose(est[0].cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    got = dict(zip(pl.COUNTER_NAMES, counters[0].tolist()))
+    assert all(abs(got[k] - c[k]) <= 1 for k in pl.COUNTER_NAMES), (got, c)

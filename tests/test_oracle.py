@@ -136,3 +136,17 @@ def test_live_reference_family_a_and_numba():
     got = nb(np.require(g['A'].T, requirements=['C']).copy(), g['pi'].copy(),
              np.require(g['probs_st'].T, requirements=['C']).copy())
     assert np.array_equal(got, want)
+
+
+def test_post_decode_restatement_hand_checked():
+    """oracle/post_oracle.py (restates TF code that cannot run here): hand-computed frames."""
+    from oracle import post_oracle as po
+    logits = np.zeros((3, 320), np.float32)             # sigmoid = 0.5 everywhere
+    bins = np.asarray([0, 10, 319])
+    voiced = np.asarray([True, False, True])
+    # frame 0: bins {0, 1} -> (0*0.5 + 0.2*0.5) / 1.0 + 23.6 = 23.7; frame 1: bins 9..11 -> 2.0 + 23.6; frame 2: {318, 319}
+    ref = np.asarray([23.7, 0.0, 23.6 + 63.7 + 12.0], np.float32)
+    est, c = po.melody_stats_np(ref, logits, bins, voiced)
+    assert np.allclose(est, [23.7, -25.6, 23.6 + 63.7], atol=1e-5)
+    assert c == dict(gt_voiced=2, gt_unvoiced=1, correct_voiced=2, incorrect_voiced=0, correct_unvoiced=1,
+                     correct_pitches_wide=1, correct_pitches_strict=1, correct_chromas_wide=2, correct_chromas_strict=2)

@@ -17,7 +17,7 @@ ALGO_NAMES = {'auto': ALGO_AUTO, 'backpointer': ALGO_BACKPOINTER, 'cluster': ALG
 EXPORTS = ['vit_version', 'vit_strerror', 'vit_last_cuda_error', 'vit_launch_count', 'vit_select_algo',
            'vit_workspace_bytes', 'vit_decode_f32', 'vit_decode_f32_ex', 'vit_upload_frames_f32',
            'vit_fb_workspace_bytes', 'vit_forward_backward_f32', 'vit_emissions_f32', 'vit_voiced_bins',
-           'vit_analyze_structure_f32', 'vit_clips_in_flight']
+           'vit_analyze_structure_f32', 'vit_clips_in_flight', 'vit_melody_stats_f32']
 
 
 class Structure(ctypes.Structure):
@@ -80,6 +80,8 @@ def load():
     L.vit_emissions_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, ctypes.c_float, ci, vp, vp]
     L.vit_voiced_bins.restype = ci
     L.vit_voiced_bins.argtypes = [vp, ctypes.c_longlong, ci, vp, vp, vp]
+    L.vit_melody_stats_f32.restype = ci
+    L.vit_melody_stats_f32.argtypes = [vp, ci, ci, vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ctypes.c_float, vp, vp, vp]
     L.vit_upload_frames_f32.restype = ci
     L.vit_upload_frames_f32.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
     _lib = L

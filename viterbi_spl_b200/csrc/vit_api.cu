@@ -59,6 +59,9 @@ int fb_run(const float* A, const float* pi, const float* lik, const int32_t* len
 int emissions_run(const float* logits, const float* prior, int B, int T, int n_bins, int model, int spw, float threshold,
                   int out_log, float* out, cudaStream_t stream);
 int voiced_bins_run(const int64_t* states, long long n, int n_bins, uint8_t* voiced, int64_t* bins, cudaStream_t stream);
+int melody_stats_run(const float* logits, int logit_stride, int logit_offset, const float* ref_notes, const int64_t* bins,
+                     const uint8_t* voiced, const int32_t* lengths, int B, int T, int n_bins, float note_min,
+                     float note_step, float* est_notes, int64_t* counters, cudaStream_t stream);
 
 // vit_banded.cu
 bool banded_supported(int S, const vit_structure* st);
@@ -258,6 +261,19 @@ int vit_emissions_f32(const float* d_logits, const float* d_prior, int B, int T,
 int vit_voiced_bins(const int64_t* d_states, long long n, int n_bins, uint8_t* d_voiced, int64_t* d_bins, void* stream) {
   if (n < 0 || n_bins < 1 || ((!d_states || !d_voiced || !d_bins) && n > 0)) return VIT_ERR_INVALID_ARGUMENT;
   return voiced_bins_run(d_states, n, n_bins, d_voiced, d_bins, (cudaStream_t)stream);
+}
+
+int vit_melody_stats_f32(const float* d_logits, int logit_stride, int logit_offset, const float* d_ref_notes,
+                         const int64_t* d_bins, const uint8_t* d_voiced, const int32_t* d_lengths, int B, int T,
+                         int n_bins, float note_min, float note_step, float* d_est_notes, int64_t* d_counters,
+                         void* stream) {
+  if (B < 0 || T < 1 || n_bins < 1 || logit_offset < 0 || logit_stride < logit_offset + n_bins)
+    return VIT_ERR_INVALID_ARGUMENT;
+  if (B > 65535) return VIT_ERR_INVALID_ARGUMENT;   // one grid row per clip
+  if (B > 0 && (!d_logits || !d_ref_notes || !d_bins || !d_voiced || !d_est_notes || !d_counters))
+    return VIT_ERR_INVALID_ARGUMENT;
+  return melody_stats_run(d_logits, logit_stride, logit_offset, d_ref_notes, d_bins, d_voiced, d_lengths, B, T, n_bins,
+                          note_min, note_step, d_est_notes, d_counters, (cudaStream_t)stream);
 }
 
 int vit_analyze_structure_f32(const float* h_logA_T, int S, vit_structure* out) {

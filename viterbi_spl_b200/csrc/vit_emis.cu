@@ -6,6 +6,9 @@
 //       VIT_EMIS_SHAUN    Viterbi.observation_probs_fn          tonet/softmax_priors.py:1722-1786 (max-subtracted
 //                         form; dcnet/softmax_viterbi.py:2316-2359 is the same model)
 //   vit_voiced_bins     states -> (voiced, bins)                dcnet/softmax_viterbi.py:2427-2431
+//   vit_melody_stats_f32  (bins, voiced, logits, ref notes) -> refined note per frame + the nine frame counters of
+//                         MetricsInference.viterbi_update_states_tf_fn, dcnet/softmax_viterbi.py:2923-2979
+//                         (est_notes_fn: dcnet/main.py:1911-1934)
 //
 // Peak picking is exact (comparisons only): bin k is a peak iff np.argmax of the reflect-padded window
 // [k - spw, k + spw] returns the centre, i.e. every left neighbour is STRICTLY smaller and every right neighbour is
@@ -212,6 +215,75 @@ __global__ void voiced_bins_kernel(const int64_t* __restrict__ states, long long
   }
 }
 
+
+// ---- post-decode statistics ---------------------------------------------------------------------------------------
+// Per frame (est_notes_fn, dcnet/main.py:1911-1934): probs = sigmoid(logits); the decoded bin and its two neighbours
+// (|k - bin| <= 1, clipped to the bin range) give
+//     note = sum_k (k * note_step) * p_k / max(sum_k p_k, 1e-3) + note_min
+// then (viterbi_update_states_tf_fn, dcnet/softmax_viterbi.py:2938-2977) with ref_voicing = ref_note > 0.1,
+// diff = |note - ref_note|:  voiced / unvoiced reference frames, correct / incorrect voiced and correct unvoiced
+// decisions, pitch hits (diff < 0.5 on voiced reference frames; "strict" = also decoded voiced) and chroma hits
+// (|diff - 12 floor(diff / 12 + 0.5)| < 0.5).  Output note = +note where decoded voiced, -note elsewhere (:2975).
+// One thread per frame (3 logits, one note, one bin of a 1.3-1.4 KB row: the kernel moves ~50 B per frame);
+// counters are reduced per warp and added with one 64-bit atomic per warp and counter.
+constexpr int kStatCounters = 9;
+
+__global__ void melody_stats_kernel(const float* __restrict__ logits, int logit_stride, int logit_offset,
+                                    const float* __restrict__ ref_notes, const int64_t* __restrict__ bins,
+                                    const uint8_t* __restrict__ voiced, const int32_t* __restrict__ lengths, int T,
+                                    int n_bins, float note_min, float note_step, float* __restrict__ est_notes,
+                                    unsigned long long* __restrict__ counters) {
+  const int b = blockIdx.y;
+  const int len = lengths ? lengths[b] : T;
+  const int lane = threadIdx.x & 31;
+  unsigned cnt[kStatCounters];
+#pragma unroll
+  for (int k = 0; k < kStatCounters; ++k) cnt[k] = 0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    const size_t f = (size_t)b * T + t;
+    if (t >= len) {
+      est_notes[f] = 0.f;
+      continue;
+    }
+    const int64_t bin64 = bins[f];
+    const int bin = (int)(bin64 < 0 ? 0 : (bin64 >= n_bins ? n_bins - 1 : bin64));
+    const bool ev = voiced[f] != 0;
+    const float* row = logits + f * (size_t)logit_stride + logit_offset;
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int d = -1; d <= 1; ++d) {
+      const int k = bin + d;
+      if (k >= 0 && k < n_bins) {
+        const float p = 1.f / (1.f + expf(-row[k]));
+        num = __fadd_rn(num, __fmul_rn(__fmul_rn((float)k, note_step), p));
+        den = __fadd_rn(den, p);
+      }
+    }
+    const float note = __fadd_rn(__fdiv_rn(num, fmaxf(den, 1e-3f)), note_min);
+    est_notes[f] = ev ? note : -note;
+    const float ref = ref_notes[f];
+    const bool rv = ref > 0.1f;
+    const float diff = fabsf(note - ref);
+    const bool pitch = rv && diff < 0.5f;
+    const float oct = floorf(diff / 12.f + 0.5f) * 12.f;
+    const bool chroma = rv && fabsf(diff - oct) < 0.5f;
+    cnt[0] += rv;
+    cnt[1] += !rv;
+    cnt[2] += rv && ev;
+    cnt[3] += !rv && ev;
+    cnt[4] += !rv && !ev;
+    cnt[5] += pitch;
+    cnt[6] += pitch && ev;
+    cnt[7] += chroma;
+    cnt[8] += chroma && ev;
+  }
+#pragma unroll
+  for (int k = 0; k < kStatCounters; ++k) {
+    const unsigned v = __reduce_add_sync(0xffffffffu, cnt[k]);
+    if (lane == 0 && v) atomicAdd(&counters[(size_t)b * kStatCounters + k], (unsigned long long)v);
+  }
+}
+
 int emissions_run(const float* logits, const float* prior, int B, int T, int n_bins, int model, int spw, float threshold,
                   int out_log, float* out, cudaStream_t stream) {
   const long long n_frames = (long long)B * T;
@@ -246,6 +318,21 @@ int voiced_bins_run(const int64_t* states, long long n, int n_bins, uint8_t* voi
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   voiced_bins_kernel<<<(unsigned)blocks, 256, 0, stream>>>(states, n, n_bins, voiced, bins);
+  note_launch();
+  VIT_CUDA_TRY(cudaGetLastError());
+  return VIT_OK;
+}
+
+int melody_stats_run(const float* logits, int logit_stride, int logit_offset, const float* ref_notes, const int64_t* bins,
+                     const uint8_t* voiced, const int32_t* lengths, int B, int T, int n_bins, float note_min,
+                     float note_step, float* est_notes, int64_t* counters, cudaStream_t stream) {
+  if (B == 0) return VIT_OK;
+  VIT_CUDA_TRY(cudaMemsetAsync(counters, 0, (size_t)B * kStatCounters * sizeof(int64_t), stream));
+  int gx = (T + 255) / 256;
+  if (gx > 64) gx = 64;
+  melody_stats_kernel<<<dim3(gx, B), 256, 0, stream>>>(logits, logit_stride, logit_offset, ref_notes, bins, voiced,
+                                                        lengths, T, n_bins, note_min, note_step, est_notes,
+                                                        reinterpret_cast<unsigned long long*>(counters));
   note_launch();
   VIT_CUDA_TRY(cudaGetLastError());
   return VIT_OK;

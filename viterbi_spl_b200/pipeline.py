@@ -58,6 +58,36 @@ def voiced_bins_device(states, n_bins):
     return voiced.bool(), bins
 
 
+COUNTER_NAMES = ('gt_voiced', 'gt_unvoiced', 'correct_voiced', 'incorrect_voiced', 'correct_unvoiced',
+                 'correct_pitches_wide', 'correct_pitches_strict', 'correct_chromas_wide', 'correct_chromas_strict')
+
+
+def melody_stats_device(logits, ref_notes, bins, voiced, lengths=None, n_bins=None, logit_offset=0, note_min=23.6,
+                        note_step=0.2):
+    """The statistics step after the decode (MetricsInference.viterbi_update_states_tf_fn,
+    dcnet/softmax_viterbi.py:2923-2979), batched: logits CUDA float32 [B, T, W] (bin k = column logit_offset + k),
+    ref_notes float32 [B, T], bins int64 [B, T] and voiced bool/uint8 [B, T] as MelodyPipeline returns them ->
+    (est_notes_with_voicing_info float32 [B, T], counters int64 [B, 9] in COUNTER_NAMES order)."""
+    assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous() and logits.ndim == 3
+    B, T, W = logits.shape
+    n_bins = W - logit_offset if n_bins is None else int(n_bins)
+    ref_notes = ref_notes.to(logits.device, torch.float32).contiguous()
+    bins = bins.to(logits.device, torch.int64).contiguous()
+    voiced = voiced.to(logits.device).to(torch.uint8).contiguous()
+    assert ref_notes.shape == (B, T) and bins.shape == (B, T) and voiced.shape == (B, T)
+    if lengths is not None:
+        lengths = torch.as_tensor(lengths).to(logits.device, torch.int32).contiguous()
+    est = torch.empty((B, T), dtype=torch.float32, device=logits.device)
+    counters = torch.empty((B, len(COUNTER_NAMES)), dtype=torch.int64, device=logits.device)
+    with torch.cuda.device(logits.device):
+        st = torch.cuda.current_stream()
+        _lib.check(_lib.load().vit_melody_stats_f32(_ptr(logits), W, int(logit_offset), _ptr(ref_notes), _ptr(bins),
+                                                    _ptr(voiced), _ptr(lengths), B, T, n_bins, float(note_min),
+                                                    float(note_step), _ptr(est), _ptr(counters),
+                                                    ctypes.c_void_p(st.cuda_stream)))
+    return est, counters
+
+
 class MelodyPipeline:
     """logits [B, T, *] -> (voiced [B, T] bool, bins [B, T] int64) entirely on the GPU.
 
@@ -92,3 +122,17 @@ class MelodyPipeline:
         states, _ = self.decoder.decode_device(E, lengths)
         voiced, bins = voiced_bins_device(states, self.n_bins)
         return (voiced[0], bins[0]) if squeeze else (voiced, bins)
+
+    def evaluate(self, logits, ref_notes, lengths=None, note_min=23.6, note_step=0.2):
+        """logits [B, T, *] + reference notes [B, T] -> (voiced, bins, est_notes_with_voicing_info, counters [B, 9]):
+        emissions, decode, voiced/bins and the frame statistics of dcnet/softmax_viterbi.py:3033-3046 in one go, all
+        on the GPU."""
+        logits = torch.as_tensor(logits).to(self.device, torch.float32).contiguous()
+        assert logits.ndim == 3
+        if lengths is not None:
+            lengths = torch.as_tensor(lengths).to(self.device, torch.int32).contiguous()
+        voiced, bins = self(logits, lengths)
+        off = 1 if self.model == SOFTMAX else 0
+        est, counters = melody_stats_device(logits, torch.as_tensor(ref_notes), bins, voiced, lengths, self.n_bins, off,
+                                            note_min, note_step)
+        return voiced, bins, est, counters
