@@ -30,7 +30,7 @@
 #include <type_traits>
 #include <vector>
 
-#include "vit_common.cuh"
+#include "vit_tmem.cuh"
 
 namespace vit {
 
@@ -75,6 +75,15 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
   constexpr int DP = (D + 3) / 4 * 4;
   constexpr int U0 = DP - D;                         // window element of cell (r, n) = w[U0 + r + n]
   constexpr int NW4 = (U0 + W - 1 + bNJ + 3) / 4;    // float4s in a thread's window
+  // 4 x 29 band entries + everything else do not fit 168 registers: ptxas spills 12 words and the reloads cost 28 % of
+  // the step (measured: the D = 14 instance on a +-12 matrix, 4.80 vs 3.75 ms).  So for D > 12 the last SPL offsets of
+  // every target live in TENSOR MEMORY (16 columns of this thread's own lane; idle silicon in a SIMT kernel) and come
+  // back once per step with one tcgen05.ld, issued at the top of the step and awaited where the sweep first needs them.
+  constexpr int SPL = D > 12 ? 4 : 0;
+  constexpr int WR = W - SPL;                        // band offsets kept in registers
+  constexpr int M_WAIT = (WR + U0 - 3 + 3) / 4;      // first window float4 with a cell at offset r >= WR
+  constexpr int kTmemColsBanded = 64;                // 3 warp groups x 16 columns, rounded up to a power of two
+  __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_delta[bCS][2][bCPT][bRowLen];
   __shared__ float s_partM[bCS][2][bTGW][bCPT];
   __shared__ float s_partD[bCS][2][bTGW][bCPT];
@@ -88,21 +97,44 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
   // ---- one-time: my band entries -> registers; dense-column and dense-row entries --------------------------------
   // a[n][r] = logA^T[j0+n][j0+n + r - D]; entries that fall outside the matrix, on the dense state's row or on the
   // dense state's column are -inf (the dense column has its own term, the dense row its own code)
-  float a[bNJ][W], acol[bNJ], arow[bNJ];
+  float a[bNJ][WR], acol[bNJ], arow[bNJ];
   bool jn_ok[bNJ];
+  uint32_t taddr = 0;
+  if constexpr (SPL > 0) {
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(&s_tmem_base)), "n"(kTmemColsBanded) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // my lane of quadrant warp & 3, 16 columns of warp group warp >> 2 (uniform per warp)
+    taddr = __shfl_sync(0xffffffffu, s_tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 16), 0);
+  }
 #pragma unroll
   for (int n = 0; n < bNJ; ++n) {
     const int j = j0 + n;
     const bool jok = j < S && j != jd;
     jn_ok[n] = jok;
 #pragma unroll
-    for (int r = 0; r < W; ++r) {
+    for (int r = 0; r < WR; ++r) {
       const int i = j + r - D;
       a[n][r] = (jok && i >= 0 && i < S && i != jd) ? logA_T[(size_t)j * S + i] : -INFINITY;
+    }
+    if constexpr (SPL > 0) {
+      float hi[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = j + WR + k - D;
+        hi[k] = (jok && i >= 0 && i < S && i != jd) ? logA_T[(size_t)j * S + i] : -INFINITY;
+      }
+      tmem_st4(taddr + 4 * n, make_float4(hi[0], hi[1], hi[2], hi[3]));
     }
     acol[n] = (jok && jd >= 0) ? logA_T[(size_t)j * S + jd] : -INFINITY;   // dense source column: A[jd -> j]
     arow[n] = (jok && jd >= 0) ? logA_T[(size_t)jd * S + j] : -INFINITY;   // dense target row:    A[j -> jd]
   }
+  if constexpr (SPL > 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   const float a_dd = jd >= 0 ? logA_T[(size_t)jd * S + jd] : -INFINITY;
   // a warp whose 128 targets are all band states takes the unpredicated loads / stores
   const bool wfull = __all_sync(0xffffffffu, jn_ok[0] && jn_ok[1] && jn_ok[2] && jn_ok[3]);
@@ -196,16 +228,23 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
           // the band: my window of delta_{t-1} is NW4 aligned float4s starting at my own targets' slot.  One float4 at
           // a time, applied to every (offset r, target n) cell that reads it: only 4 window values are ever live
           const float4* row4 = reinterpret_cast<const float4*>(prev) + tg;
+          float ah[16];                                      // band offsets WR.. of my 4 targets
 #pragma unroll
           for (int m = 0; m < NW4; ++m) {
             const float4 v = row4[m];
             const float wv[4] = {v.x, v.y, v.z, v.w};
+            if constexpr (SPL > 0) {
+              // (short-lived on purpose: fetched per clip two float4s ahead of the first cell that needs them)
+              if (m == M_WAIT - 2) tmem_ld<16>(taddr, ah);
+              if (m == M_WAIT) tmem_wait_ld<16>(ah);
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
 #pragma unroll
               for (int n = 0; n < bNJ; ++n) {
                 const int r = 4 * m + k - U0 - n;                    // cell (r, n) reads window element U0 + r + n
-                if (r >= 0 && r < W) acc[c][n] = fmaxf(acc[c][n], __fadd_rn(wv[k], a[n][r]));
+                if (r >= 0 && r < WR) acc[c][n] = fmaxf(acc[c][n], __fadd_rn(wv[k], a[n][r]));
+                else if (r >= WR && r < W) acc[c][n] = fmaxf(acc[c][n], __fadd_rn(wv[k], ah[n * 4 + (r - WR)]));
               }
           }
           // combine the per-warp partials of step t-1: max_{i != jd} delta_{t-1}[i] and the dense target row's
@@ -276,6 +315,12 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
     if (ncl >= 2) run_pass(std::integral_constant<int, 2>{}, seq0);
     else if (ncl == 1) run_pass(std::integral_constant<int, 1>{}, seq0);
   }
+  if constexpr (SPL > 0) {
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem_base), "n"(kTmemColsBanded) : "memory");
+  }
 }
 
 // vit_cluster.cu
@@ -284,6 +329,10 @@ int launch_hist_backtrace(const float* logA_T, const float* hist, const int32_t*
 
 static int banded_template_D(int d) {
   const int opts[] = {4, 8, 12, 14};
+  if (const char* f = getenv("VIT_BANDED_FORCE_D")) {         // experiment knob: a wider instance than the band needs
+    const int fd = atoi(f);
+    for (int o : opts) if (o == fd && d <= o) return o;
+  }
   for (int o : opts) if (d <= o) return o;
   return -1;
 }
