@@ -13,6 +13,7 @@
 // (6 targets = 24 bytes per thread: 8-byte aligned, conflict-free per half warp); dense (unvoiced) row and max_i delta_i
 // as per-warp partials combined after the step's single barrier, exactly as in vit_banded.cu.
 #include <cstdlib>
+#include <type_traits>
 
 #include "vit_tmem.cuh"
 
@@ -57,7 +58,9 @@ template <int D>
 __global__ void __launch_bounds__(wThreads, 1)
 wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ logA_T, const float* __restrict__ log_pi,
                     const float* __restrict__ log_emis, const int32_t* __restrict__ lengths, int B, int T_max, int S,
-                    int jd, float cbg, float* __restrict__ hist, int t_begin, int t_end) {
+                    int jd, float cbg, float* __restrict__ hist, int t_begin, int t_end, int q) {
+  // q: clips per CTA and pass (1..8), spread evenly by the host; pipeline cs takes clips [4 cs, 4 cs + 4) of them and
+  // runs the 4-, 2- or 1-clip instance of the step (a single recording costs a quarter of the cells of a full pipeline)
   constexpr int W = 2 * D + 1, NCH = (W + 3) / 4;
   constexpr int DP = (D + 1) / 2 * 2;                // delta row: state i at float index i + DP (even: 8-byte aligned windows)
   constexpr int U0 = DP - D;                         // window element of cell (r, n) = w[U0 + r + n]
@@ -105,29 +108,24 @@ wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ 
   tc_fence_after();
   const long long hist_delta = reinterpret_cast<const char*>(hist) - reinterpret_cast<const char*>(log_emis);
 
-  for (int seq0 = blockIdx.x * wMB; seq0 < B; seq0 += gridDim.x * wMB) {
-    __syncthreads();
-    if (tid < wMB) {
-      const int b = seq0 + tid;
-      s_len[tid] = b < B ? (lengths ? lengths[b] : T_max) : 0;
-    }
-    for (int x = tid; x < wCS * 2 * wCPT * ROW; x += wThreads) smem[x] = -INFINITY;     // pads stay -inf
-    __syncthreads();
-    const int c0 = cs * wCPT;
-    int len[wCPT];
+  const int c0 = cs * wCPT;
+  const int ncl = min(wCPT, q - c0);                         // clips of this pipeline (<= 0: idle)
+  auto run_pass = [&](auto cpt_tag, int seq0) {
+    constexpr int CPT = decltype(cpt_tag)::value;
+    int len[CPT];
     int maxlen = 0;
 #pragma unroll
-    for (int c = 0; c < wCPT; ++c) { len[c] = s_len[c0 + c]; maxlen = max(maxlen, len[c]); }
-    const float* pe[wCPT];
+    for (int c = 0; c < CPT; ++c) { len[c] = s_len[c0 + c]; maxlen = max(maxlen, len[c]); }
+    const float* pe[CPT];
 #pragma unroll
-    for (int c = 0; c < wCPT; ++c) pe[c] = log_emis + ((size_t)(seq0 + c0 + c) * T_max + t_begin) * S + j0;
+    for (int c = 0; c < CPT; ++c) pe[c] = log_emis + ((size_t)(seq0 + c0 + c) * T_max + t_begin) * S + j0;
     const int jd_off = jd - j0;
     const int t_stop = min(maxlen, t_end);
     if (t_begin > 0 && t_begin < t_stop) {
       // resume a frame range from the history (see vit_banded.cu)
       const int pb = (t_begin - 1) & 1;
 #pragma unroll
-      for (int c = 0; c < wCPT; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         const float* row = hist + ((size_t)(seq0 + c0 + c) * T_max + (t_begin - 1)) * S;
         const bool lv = t_begin - 1 < len[c];
         float mloc = -INFINITY;
@@ -147,30 +145,30 @@ wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ 
       wpipe_bar_sync(cs);
     }
 
-    float ed_prev[wCPT];
+    float ed_prev[CPT];
 #pragma unroll
-    for (int c = 0; c < wCPT; ++c) ed_prev[c] = 0.f;
+    for (int c = 0; c < CPT; ++c) ed_prev[c] = 0.f;
     for (int t = t_begin; t < t_stop; ++t) {
       const int buf = t & 1;
 #pragma unroll
-      for (int c = 0; c < wCPT; ++c) asm volatile("" : "+l"(pe[c]));
-      bool live[wCPT];
+      for (int c = 0; c < CPT; ++c) asm volatile("" : "+l"(pe[c]));
+      bool live[CPT];
 #pragma unroll
-      for (int c = 0; c < wCPT; ++c) live[c] = t < len[c];
-      float e[wCPT][wNJ], ed[wCPT];
+      for (int c = 0; c < CPT; ++c) live[c] = t < len[c];
+      float e[CPT][wNJ], ed[CPT];
 #pragma unroll
-      for (int c = 0; c < wCPT; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         if ((lane & 3) == 0 && t + 4 < len[c]) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe[c] + 4 * (size_t)S));
 #pragma unroll
         for (int n = 0; n < wNJ; ++n) e[c][n] = (live[c] && jn_ok[n]) ? __ldg(pe[c] + n) : 0.f;
         ed[c] = (lane == 0 && live[c] && jd >= 0) ? __ldg(pe[c] + jd_off) : 0.f;
       }
 
-      float acc[wCPT][wNJ], pd[wCPT], xd[wCPT];
+      float acc[CPT][wNJ], pd[CPT], xd[CPT];
       if (t == 0) {
         // T1[0] = log_pi + logE[0]                                                              (imm/tf_viterbi.py:94)
 #pragma unroll
-        for (int c = 0; c < wCPT; ++c) {
+        for (int c = 0; c < CPT; ++c) {
 #pragma unroll
           for (int n = 0; n < wNJ; ++n) acc[c][n] = jn_ok[n] ? log_pi[j0 + n] : -INFINITY;
           pd[c] = jd >= 0 ? log_pi[jd] : -INFINITY;
@@ -179,7 +177,7 @@ wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ 
       } else {
         const float* prev = sD + (size_t)((buf ^ 1) * wCPT) * ROW;
 #pragma unroll
-        for (int c = 0; c < wCPT; ++c) {
+        for (int c = 0; c < CPT; ++c) {
           const float* pm = &s_partM[cs][buf ^ 1][0][c];
           const float* pdd = &s_partD[cs][buf ^ 1][0][c];
           float dm = fmaxf(fmaxf(pm[0], pm[wCPT]), fmaxf(pm[2 * wCPT], pm[3 * wCPT]));
@@ -203,10 +201,10 @@ wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ 
         }
         // the band: chunks of 4 offsets x 6 targets from TMEM (one chunk ahead), each applied to my 4 clips; the window
         // of delta_{t-1} slides by 4 per chunk (two LDS.64 per clip per chunk)
-        float win[wCPT][wNJ + 4 + 2];                  // w[U0 + 4c .. U0 + 4c + 9] of each clip (U0 <= 1)
-        const float* wbase[wCPT];
+        float win[CPT][wNJ + 4 + 2];                  // w[U0 + 4c .. U0 + 4c + 9] of each clip (U0 <= 1)
+        const float* wbase[CPT];
 #pragma unroll
-        for (int c = 0; c < wCPT; ++c) {
+        for (int c = 0; c < CPT; ++c) {
           wbase[c] = prev + (size_t)c * ROW + j0;     // float index of window element 0 (8-byte aligned)
 #pragma unroll
           for (int k = 0; k < (wNJ + 4 + 2) / 2; ++k) {
@@ -223,7 +221,7 @@ wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ 
           tmem_wait_ld<24>(a);
           if (ch + 1 < NCH) tmem_ld_chunk<24>(tbase + (ch + 1) * 24, an);
 #pragma unroll
-          for (int c = 0; c < wCPT; ++c) {
+          for (int c = 0; c < CPT; ++c) {
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
@@ -244,7 +242,7 @@ wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ 
       // T1[t][j] = max + logE[t][j]                                                              (:100)
       float pm[wCPT];
 #pragma unroll
-      for (int c = 0; c < wCPT; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         float v[wNJ];
         float mloc = -INFINITY;
 #pragma unroll
@@ -264,13 +262,13 @@ wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ 
       }
       if (lane == 0) {
 #pragma unroll
-        for (int c = 0; c < wCPT; ++c) {
+        for (int c = 0; c < CPT; ++c) {
           s_partM[cs][buf][Q][c] = pm[c];
           s_partD[cs][buf][Q][c] = pd[c];
         }
       }
 #pragma unroll
-      for (int c = 0; c < wCPT; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         ed_prev[c] = ed[c];
         pe[c] += S;
       }
@@ -280,7 +278,7 @@ wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ 
     if (jd >= 0 && t_stop > t_begin && Q == 0 && lane == 0) {
       const int buf = (t_stop - 1) & 1;
 #pragma unroll
-      for (int c = 0; c < wCPT; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         if (t_stop - 1 < len[c]) {
           const float* pdd = &s_partD[cs][buf][0][c];
           const float x = __fadd_rn(fmaxf(fmaxf(pdd[0], pdd[wCPT]), fmaxf(pdd[2 * wCPT], pdd[3 * wCPT])), ed_prev[c]);
@@ -288,6 +286,19 @@ wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ 
         }
       }
     }
+  };
+
+  for (int seq0 = blockIdx.x * q; seq0 < B; seq0 += gridDim.x * q) {
+    __syncthreads();
+    if (tid < wMB) {
+      const int b = seq0 + tid;
+      s_len[tid] = (tid < q && b < B) ? (lengths ? lengths[b] : T_max) : 0;
+    }
+    for (int x = tid; x < wCS * 2 * wCPT * ROW; x += wThreads) smem[x] = -INFINITY;     // pads stay -inf
+    __syncthreads();
+    if (ncl >= 3) run_pass(std::integral_constant<int, 4>{}, seq0);
+    else if (ncl == 2) run_pass(std::integral_constant<int, 2>{}, seq0);
+    else if (ncl == 1) run_pass(std::integral_constant<int, 1>{}, seq0);
   }
   tc_fence_before();
   __syncthreads();
@@ -315,7 +326,7 @@ size_t banded_wide_workspace_bytes(int B, int T_max, int S) {
 template <int D>
 static int launch_wide(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
                        int T_max, int S, int jd, float cbg, float* packed, float* hist, int t_begin, int t_end, int grid,
-                       cudaStream_t stream) {
+                       int q, cudaStream_t stream) {
   constexpr int W = 2 * D + 1, NCH = (W + 3) / 4;
   constexpr int DP = (D + 1) / 2 * 2, U0 = DP - D, NWIN = U0 + 4 * NCH + wNJ, ROW = (wMaxS + NWIN + 8) & ~1;
   size_t smem = (size_t)wCS * 2 * wCPT * ROW * sizeof(float);
@@ -324,7 +335,7 @@ static int launch_wide(const float* logA_T, const float* log_pi, const float* lo
   note_launch();
   VIT_CUDA_TRY(cudaFuncSetAttribute(wide_forward_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   wide_forward_kernel<D><<<grid, wThreads, smem, stream>>>(packed, logA_T, log_pi, log_emis, lengths, B, T_max, S, jd, cbg,
-                                                          hist, t_begin, t_end);
+                                                          hist, t_begin, t_end, q);
   note_launch();
   VIT_CUDA_TRY(cudaGetLastError());
   return VIT_OK;
@@ -336,13 +347,17 @@ int banded_wide_forward(const float* logA_T, const float* log_pi, const float* l
   int num_sms = 148, dev = 0;
   VIT_CUDA_TRY(cudaGetDevice(&dev));
   VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  const int want = (B + wMB - 1) / wMB;
+  // spread the clips evenly over the SMs (as vit_banded.cu): `passes` trips of q <= 8 clips per CTA
+  const int passes = (B + wMB * num_sms - 1) / (wMB * num_sms);
+  int q = (B + passes * num_sms - 1) / (passes * num_sms);
+  q = q < 1 ? 1 : (q > wMB ? wMB : q);
+  const int want = (B + q - 1) / q;
   const int grid = want < num_sms ? want : num_sms;
   float* packed = (float*)packed_ws;
   switch (wide_template_D(st->halfwidth)) {
-    case 20: return launch_wide<20>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, t_begin, t_end, grid, stream);
-    case 28: return launch_wide<28>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, t_begin, t_end, grid, stream);
-    case 40: return launch_wide<40>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, t_begin, t_end, grid, stream);
+    case 20: return launch_wide<20>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, t_begin, t_end, grid, q, stream);
+    case 28: return launch_wide<28>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, t_begin, t_end, grid, q, stream);
+    case 40: return launch_wide<40>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, t_begin, t_end, grid, q, stream);
     default: return VIT_ERR_UNSUPPORTED_ALGO;
   }
 }
