@@ -208,13 +208,14 @@ def test_more_clips_than_one_wave(Decoder):
 
 
 def test_jdc_and_imm_state_sets_722(Decoder):
-    for name, add_tiny in (('jdc', True), ('imm', False)):
+    for name, add_tiny in (('jdc', True), ('imm', False), ('imm_hmm', True)):
         A, pi = hmm_params.synthetic_hmm(name)
         logA_T, log_pi = hmm_params.log_params(A, pi, add_tiny=add_tiny)
         E = synth.batch('dense_softmax', 5, 50, 722, seed0=5)
         want_p, want_s = c_oracle.decode_batch_c(logA_T, log_pi, E)
-        # auto: the jdc matrix (band +-40) takes the wide banded kernel, the dense imm matrix the tmem kernel
-        for algo in ('auto', 'tmem', 'backpointer') + (('banded',) if name == 'jdc' else ()):
+        # auto: the jdc (band +-40) and imm-HMM (+-56: 8 of its 29 band chunks come from shared memory) matrices take the
+        # wide banded kernel, the dense imm matrix the tmem kernel
+        for algo in ('auto', 'tmem', 'backpointer') + (('banded',) if name != 'imm' else ()):
             p, s = Decoder(logA_T, log_pi, algo=algo).decode_host(E)
             assert np.array_equal(p, want_p) and np.array_equal(s, want_s), (name, algo)
 

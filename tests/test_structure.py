@@ -22,6 +22,9 @@ def test_reference_state_sets(cuda_lib):
     A, pi = hmm_params.synthetic_hmm('jdc')
     kind, hw, di, bg = analyze(cuda_lib, hmm_params.log_params(A, pi)[0])
     assert kind == 1 and hw == 40 and di == 721
+    A, pi = hmm_params.synthetic_hmm('imm_hmm')             # band +-56: wide kernel with a shared-memory band tail
+    kind, hw, di, bg = analyze(cuda_lib, hmm_params.log_params(A, pi)[0])
+    assert kind == 1 and hw == 56 and di == 721
     # imm: fully dense
     A, pi = hmm_params.synthetic_hmm('imm')
     kind, hw, di, bg = analyze(cuda_lib, hmm_params.log_params(A, pi, add_tiny=False)[0])
@@ -41,7 +44,7 @@ def test_hand_made_matrices(cuda_lib):
     assert analyze(cuda_lib, B) == (1, 3, 7, -50.0)
     C = A.copy()
     C[0, S - 1] = -1.0                                     # one far entry, not a dense state: the band must cover it
-    assert analyze(cuda_lib, C)[:2] == (1, S - 1)          # (39 <= 40: the wide kernel's band spans the whole 40 x 40 matrix)
+    assert analyze(cuda_lib, C)[:2] == (1, S - 1)          # (39 <= 56: the wide kernel's band spans the whole 40 x 40 matrix)
     S3 = 100
     C3 = np.full((S3, S3), -50.0, np.float32)
     for k in (-1, 0, 1):
@@ -55,8 +58,8 @@ def test_hand_made_matrices(cuda_lib):
     E = A.copy()
     E[3, 3] = np.nan
     assert analyze(cuda_lib, E)[0] == 0
-    # band of 41: too wide for either kernel; band of 20 on an odd state count: the wide kernel wants even S
-    for S2, d2, want in ((200, 41, 0), (200, 20, 1), (201, 20, 0), (201, 14, 1)):
+    # band of 57: too wide for either kernel; band of 20 on an odd state count: the wide kernel wants even S
+    for S2, d2, want in ((200, 57, 0), (200, 41, 1), (200, 20, 1), (201, 20, 0), (201, 14, 1)):
         F = np.full((S2, S2), -9.0, np.float32)
         for k in range(-d2, d2 + 1):
             idx = np.arange(max(0, -k), min(S2, S2 - k))

@@ -167,6 +167,11 @@ int vit_workspace_bytes(int B, int T_max, int S, int algo, size_t* out_bytes) {
   *out_bytes = (a == VIT_ALGO_TMEM)      ? tmem_workspace_bytes(B, T_max, S)
                : (a == VIT_ALGO_CLUSTER) ? cluster_workspace_bytes(B, T_max, S)
                                          : bp_workspace_bytes(B, T_max, S, false);
+  // VIT_ALGO_AUTO may resolve to the banded kernels at decode time (opts->structure): cover them as well
+  if (algo == VIT_ALGO_AUTO) {
+    const size_t b = banded_workspace_bytes(B, T_max, S);
+    if (b > *out_bytes) *out_bytes = b;
+  }
   return VIT_OK;
 }
 

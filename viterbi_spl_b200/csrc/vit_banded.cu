@@ -337,12 +337,12 @@ static int banded_template_D(int d) {
   return -1;
 }
 
-// vit_banded_wide.cu: band entries in tensor memory (S <= 768, d <= 40)
+// vit_banded_wide.cu: band entries in tensor memory (S <= 768, d <= 56)
 bool banded_wide_supported(int S, const vit_structure* st);
 int banded_wide_forward(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
                         int T_max, int S, const vit_structure* st, void* packed_ws, float* hist, int t_begin, int t_end,
                         cudaStream_t stream);
-constexpr size_t kWidePackedBytes = 128 * 512 * sizeof(float);
+constexpr size_t kWidePackedBytes = (128 * 512 + 8 * 6 * 128 * 4) * sizeof(float);   // TMEM image + shared-memory band tail
 
 static bool banded_narrow_supported(int S, const vit_structure* st) {
   if (!st || st->kind != 1) return false;
@@ -423,7 +423,7 @@ int banded_decode(const float* logA_T, const float* log_pi, const float* log_emi
 // Host-side structure analysis (h_logA_T is a HOST pointer).  kind = 1 iff, apart from at most one state that is both
 // a dense source column and a dense target row, every entry that differs from the minimum entry c lies within
 // |i - j| <= halfwidth and one of the two banded kernels takes the shape (S <= 384 with d <= 14: band in registers;
-// even S <= 768 with d <= 40: band in tensor memory).
+// even S <= 768 with d <= 56: band in tensor memory, chunks past 512 columns in shared memory).
 int analyze_structure(const float* A, int S, vit_structure* out) {
   out->kind = 0;
   out->halfwidth = 0;

@@ -1,5 +1,6 @@
 // VIT_ALGO_BANDED, wide variant: the structured fast path of vit_banded.cu for the 722-state sets with wide bands
-// (jdc: +-40 bins of 721, jdc/viterbi_transition_post_processing.py `d_max = 40`).
+// (jdc: +-40 bins of 721, jdc/viterbi_transition_post_processing.py `d_max = 40`; the imm HMM: +-56,
+// imm/viterbi_transition_post_processing.py:7-18 with 240 bins per octave).
 //
 // Same identity, same proof (vit_banded.cu header): with c = the minimum entry of logA^T,
 //     max_i fl(delta_i + a_ji) = max( max_{i in band(j)} fl(delta_i + a_ji), fl(delta_unv + a_j,unv), fl(max_i delta_i + c) ),
@@ -27,6 +28,12 @@ constexpr int wTGW = 4;                    // warps per pipeline = TMEM lane qua
 constexpr int wPipeThreads = 32 * wTGW;    // 128
 constexpr int wThreads = wPipeThreads * wCS;
 constexpr int wMaxS = 32 * wTGW * wNJ;     // 768
+constexpr int wChunkCols = 4 * wNJ;        // 24 TMEM columns per chunk of 4 band offsets
+constexpr int wChunksTmem = tTmemCols / wChunkCols;   // 21 chunks fit the 512 columns (d <= 40: all of them)
+// chunks past that (d = 56: 8 of 29) live in shared memory as float4 [chunk][target n][thread], like the K tail of the
+// dense tensor-memory kernel
+constexpr int wMaxTailChunks = 8;
+constexpr size_t wTailFloats = (size_t)wMaxTailChunks * wNJ * wPipeThreads * 4;
 
 __device__ __forceinline__ void wpipe_bar_sync(int cs) {
   asm volatile("bar.sync %0, %1;" ::"r"(1 + cs), "n"(wPipeThreads) : "memory");
@@ -42,11 +49,29 @@ __device__ __forceinline__ float wwarp_max(float v) {
 template <int D>
 __global__ void wide_pack_kernel(const float* __restrict__ logA_T, int S, int jd, float* __restrict__ packed) {
   constexpr int W = 2 * D + 1, NCH = (W + 3) / 4;
-  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < 128 * tTmemCols; x += gridDim.x * blockDim.x) {
-    const int col = x % tTmemCols, tg = x / tTmemCols;
-    const int c = col / 24, w = col - c * 24, n = w >> 2, rr = w & 3;
+  constexpr int NCH_T = NCH < wChunksTmem ? NCH : wChunksTmem;
+  const int total = 128 * tTmemCols + (int)wTailFloats;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < total; x += gridDim.x * blockDim.x) {
+    int c, n, rr, tg;
+    bool ok;
+    if (x < 128 * tTmemCols) {
+      const int col = x % tTmemCols;
+      tg = x / tTmemCols;
+      c = col / wChunkCols;
+      const int w = col - c * wChunkCols;
+      n = w >> 2; rr = w & 3;
+      ok = c < NCH_T;
+    } else {
+      // tail: float index ((ct * wNJ + n) * 128 + tg) * 4 + rr
+      const int y = x - 128 * tTmemCols;
+      rr = y & 3;
+      tg = (y >> 2) % wPipeThreads;
+      n = (y >> 2) / wPipeThreads % wNJ;
+      c = NCH_T + (y >> 2) / (wPipeThreads * wNJ);
+      ok = c < NCH;
+    }
     float v = -INFINITY;
-    if (c < NCH) {
+    if (ok) {
       const int r = 4 * c + rr, j = wNJ * tg + n, i = j + r - D;
       if (r < W && j < S && j != jd && i >= 0 && i < S && i != jd) v = logA_T[(size_t)j * S + i];
     }
@@ -66,7 +91,10 @@ wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ 
   constexpr int U0 = DP - D;                         // window element of cell (r, n) = w[U0 + r + n]
   constexpr int NWIN = U0 + 4 * NCH + wNJ;           // window floats a thread may touch (rounded up to even below)
   constexpr int ROW = (wMaxS + NWIN + 8) & ~1;       // floats per delta row
-  extern __shared__ __align__(16) float smem[];      // [wCS][2][wCPT][ROW]
+  constexpr int NCH_T = NCH < wChunksTmem ? NCH : wChunksTmem;
+  constexpr int NTAIL = NCH - NCH_T;                 // chunks served from shared memory
+  static_assert(NTAIL <= wMaxTailChunks, "band too wide for the packed tail");
+  extern __shared__ __align__(16) float smem[];      // [wCS][2][wCPT][ROW], then the band tail [NTAIL][wNJ][128] float4
   __shared__ float s_partM[wCS][2][wTGW][wCPT];
   __shared__ float s_partD[wCS][2][wTGW][wCPT];
   __shared__ int s_len[wMB];
@@ -98,10 +126,15 @@ wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = __shfl_sync(0xffffffffu, s_tmem_base + ((uint32_t)(Q * 32) << 16), 0);
+  float4* sTail = reinterpret_cast<float4*>(smem + (size_t)wCS * 2 * wCPT * ROW);
   if (cs == 0) {
     const float4* src = reinterpret_cast<const float4*>(packed + (size_t)tg * tTmemCols);
-    for (int x = 0; x < NCH * 24 / 4; ++x) tmem_st4(tbase + 4 * x, src[x]);
+    for (int x = 0; x < NCH_T * wChunkCols / 4; ++x) tmem_st4(tbase + 4 * x, src[x]);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  if constexpr (NTAIL > 0) {
+    const float4* src = reinterpret_cast<const float4*>(packed + (size_t)128 * tTmemCols);
+    for (int x = tid; x < NTAIL * wNJ * wPipeThreads; x += wThreads) sTail[x] = src[x];
   }
   tc_fence_before();
   __syncthreads();
@@ -218,8 +251,18 @@ wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ 
         for (int ch = 0; ch < NCH; ++ch) {
           float* a = (ch & 1) ? a1 : a0;
           float* an = (ch & 1) ? a0 : a1;
-          tmem_wait_ld<24>(a);
-          if (ch + 1 < NCH) tmem_ld_chunk<24>(tbase + (ch + 1) * 24, an);
+          if (ch < NCH_T) tmem_wait_ld<24>(a);
+          if (ch + 1 < NCH) {
+            if (ch + 1 < NCH_T) {
+              tmem_ld_chunk<24>(tbase + (ch + 1) * 24, an);
+            } else {
+#pragma unroll
+              for (int n = 0; n < wNJ; ++n) {
+                const float4 v = sTail[((ch + 1 - NCH_T) * wNJ + n) * wPipeThreads + tg];
+                an[n * 4 + 0] = v.x; an[n * 4 + 1] = v.y; an[n * 4 + 2] = v.z; an[n * 4 + 3] = v.w;
+              }
+            }
+          }
 #pragma unroll
           for (int c = 0; c < CPT; ++c) {
 #pragma unroll
@@ -307,20 +350,21 @@ wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ 
 }
 
 static int wide_template_D(int d) {
-  const int opts[] = {20, 28, 40};
+  const int opts[] = {20, 28, 40, 56};
   for (int o : opts) if (d <= o) return o;
   return -1;
 }
 
 bool banded_wide_supported(int S, const vit_structure* st) {
-  if (!st || st->halfwidth > 40 || st->halfwidth < 0) return false;
+  if (!st || st->halfwidth > 56 || st->halfwidth < 0) return false;
   if (S > wMaxS || S < 2 || (S & 1)) return false;          // even S: every clip row starts 8-byte aligned
   if (st->dense_index < -1 || st->dense_index >= S) return false;
   return wide_template_D(st->halfwidth) > 0;
 }
 
 size_t banded_wide_workspace_bytes(int B, int T_max, int S) {
-  return align_up((size_t)128 * tTmemCols * sizeof(float), 256) + align_up((size_t)B * T_max * S * sizeof(float), 256);
+  return align_up(((size_t)128 * tTmemCols + wTailFloats) * sizeof(float), 256) +
+         align_up((size_t)B * T_max * S * sizeof(float), 256);
 }
 
 template <int D>
@@ -329,7 +373,8 @@ static int launch_wide(const float* logA_T, const float* log_pi, const float* lo
                        int q, cudaStream_t stream) {
   constexpr int W = 2 * D + 1, NCH = (W + 3) / 4;
   constexpr int DP = (D + 1) / 2 * 2, U0 = DP - D, NWIN = U0 + 4 * NCH + wNJ, ROW = (wMaxS + NWIN + 8) & ~1;
-  size_t smem = (size_t)wCS * 2 * wCPT * ROW * sizeof(float);
+  constexpr int NTAIL = NCH > wChunksTmem ? NCH - wChunksTmem : 0;
+  size_t smem = (size_t)wCS * 2 * wCPT * ROW * sizeof(float) + (size_t)NTAIL * wNJ * wPipeThreads * 16;
   if (smem < 120 * 1024) smem = 120 * 1024;                  // one CTA per SM: each allocates all 512 TMEM columns
   wide_pack_kernel<D><<<64, 256, 0, stream>>>(logA_T, S, jd, packed);
   note_launch();
@@ -358,6 +403,7 @@ int banded_wide_forward(const float* logA_T, const float* log_pi, const float* l
     case 20: return launch_wide<20>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, t_begin, t_end, grid, q, stream);
     case 28: return launch_wide<28>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, t_begin, t_end, grid, q, stream);
     case 40: return launch_wide<40>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, t_begin, t_end, grid, q, stream);
+    case 56: return launch_wide<56>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, t_begin, t_end, grid, q, stream);
     default: return VIT_ERR_UNSUPPORTED_ALGO;
   }
 }

@@ -185,7 +185,8 @@ def synthetic_p_steady(n_bins, p_unvoiced=0.56, seed=0):
 def synthetic_hmm(state_set, seed=0):
     """(A [S,S] f32/f64 row-stochastic, pi [S]) for a named state set:
     'dcnet' S=321 (d_max 12, floor 6), 'tonet' S=361 (d_max 14, floor 2), 'jdc' S=722 (d_max 40, floor 6),
-    'imm' S=722 fully dense (imm/transition_matrix.py recipe with b=20, uniform pi as imm/tf_imm.py:62-67)."""
+    'imm' S=722 fully dense (imm/transition_matrix.py recipe with b=20, uniform pi as imm/tf_imm.py:62-67),
+    'imm_hmm' S=722 banded (imm/viterbi_transition_post_processing.py:7-18: 240 bins per octave -> d_max 56, floor 2)."""
     if state_set == 'imm':
         n = 721
         return dense_imm_transition_matrix(20, n), np.full([n + 1], 1. / (n + 1))
@@ -193,6 +194,7 @@ def synthetic_hmm(state_set, seed=0):
         'dcnet': (320, 12, 6, SWITCH_DCNET, 3e-4),
         'tonet': (360, single_side_d_max(0.01, 60), 2, SWITCH_TONET, None),
         'jdc': (721, 40, 6, SWITCH_TONET, None),
+        'imm_hmm': (721, single_side_d_max(0.01, 240), 2, SWITCH_DCNET, None),
     }[state_set]
     A = banded_transition_matrix(synthetic_jump_counts(d_max, seed), n, floor, switch)
     pi = floored_init_probs(synthetic_p_steady(n, seed=seed), p_floor)
