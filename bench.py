@@ -258,7 +258,8 @@ def run_ours(a):
     # the bit-exact structured fast path that algo='auto' would take for this banded matrix is reported separately
     algo = a.algo
     if algo == 'dense':
-        algo = 'tmem' if _lib.load().vit_select_algo(a.clips, a.frames, a.states) == _lib.ALGO_TMEM else 'auto'
+        # (vit_select_algo names the DENSE kernel auto would take for this shape: tmem, or stream for big state sets)
+        algo = {v: k for k, v in _lib.ALGO_NAMES.items()}.get(_lib.load().vit_select_algo(a.clips, a.frames, a.states), 'auto')
     dec = ViterbiDecoder(logA_T, log_pi, device=dev, algo=algo)
     emis = synth.device_dense_softmax(B, T, S, seed=1234 + rank, device=dev)      # 4.4 GB: far larger than the 126 MB L2
     paths = torch.empty((B, T), dtype=torch.int64, device=dev)
@@ -386,8 +387,9 @@ def run_ours(a):
     except Exception:
         pass
     algo_res = dec.algo if dec.algo else _lib.load().vit_select_algo(B, T, S)
-    algo_name = {1: 'backpointer', 2: 'cluster', 3: 'tmem'}.get(algo_res, str(algo_res))
-    kernel_name = {1: 'bp_forward_kernel', 2: 'cluster_forward_kernel', 3: 'tmem_forward_kernel'}.get(algo_res, '?')
+    algo_name = {1: 'backpointer', 2: 'cluster', 3: 'tmem', 4: 'banded', 5: 'stream'}.get(algo_res, str(algo_res))
+    kernel_name = {1: 'bp_forward_kernel', 2: 'cluster_forward_kernel', 3: 'tmem_forward_kernel',
+                   4: 'banded_forward_kernel', 5: 'stream_forward_kernel'}.get(algo_res, '?')
     roofline = {'bound': 'fp32_alu', 'kernel': kernel_name, 'achieved': cells_per_s / 1e12,
                 'peak': alu_peak / 1e12, 'unit': 'Tcell/s', 'frac': cells_per_s / alu_peak,
                 'peak_definition': f'148 SMs x 64 cells/clk (FADD+FMNMX, 2 issue slots per cell) x {sm_mhz_peak:.0f} MHz '

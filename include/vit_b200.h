@@ -59,7 +59,12 @@ typedef enum vit_algo {
    * background, i.e. every matrix the reference's builders produce): S (2d + 3) instead of S^2 cells per frame.  Band
    * in registers for S <= 384, d <= 14 (dcnet / msnet / ftanet / tonet); band in tensor memory for even S <= 768,
    * d <= 40 (jdc).  Needs opts->structure from vit_analyze_structure_f32; VIT_ALGO_AUTO picks it when that says kind = 1. */
-  VIT_ALGO_BANDED = 4
+  VIT_ALGO_BANDED = 4,
+  /* dense recursion with logA^T STREAMED from L2: one CTA per SM owns 14 clips and all S targets, a producer warp feeds
+   * 24 KB tiles of the pre-packed matrix through a 4-stage TMA (cp.async.bulk) ring; no clusters, no exchange, all 148
+   * SMs busy whatever S is (S <= 1152).  The big-batch path for big state sets (BASELINE config 3: S = 722); needs
+   * >= 14 clips per SM to fill the machine.  Supports frame ranges. */
+  VIT_ALGO_STREAM = 5
 } vit_algo;
 
 /* Structure of a transition matrix as found by vit_analyze_structure_f32 (see csrc/vit_banded.cu for the proof that

@@ -20,7 +20,7 @@ from viterbi_spl_b200 import hmm_params, synth
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
-ALGOS = ['tmem', 'cluster', 'backpointer']
+ALGOS = ['tmem', 'cluster', 'backpointer', 'stream']
 
 
 def load(name):
@@ -46,7 +46,7 @@ def algos_for(S):
     if S <= 364:
         return ALGOS
     tmem_ok = _lib.load().vit_select_algo(1, 1, S) == _lib.ALGO_TMEM
-    return ['tmem', 'backpointer', 'auto'] if tmem_ok else ['backpointer', 'auto']
+    return ['tmem', 'backpointer', 'auto', 'stream'] if tmem_ok else ['backpointer', 'auto', 'stream']
 
 
 # ---- golden vectors (made by the reference's own code) ------------------------------------------------------------
@@ -215,7 +215,7 @@ def test_jdc_and_imm_state_sets_722(Decoder):
         want_p, want_s = c_oracle.decode_batch_c(logA_T, log_pi, E)
         # auto: the jdc (band +-40) and imm-HMM (+-56: 8 of its 29 band chunks come from shared memory) matrices take the
         # wide banded kernel, the dense imm matrix the tmem kernel
-        for algo in ('auto', 'tmem', 'backpointer') + (('banded',) if name != 'imm' else ()):
+        for algo in ('auto', 'tmem', 'stream', 'backpointer') + (('banded',) if name != 'imm' else ()):
             p, s = Decoder(logA_T, log_pi, algo=algo).decode_host(E)
             assert np.array_equal(p, want_p) and np.array_equal(s, want_s), (name, algo)
 
@@ -324,6 +324,8 @@ def test_frame_slabs_resume_from_the_delta_history(Decoder, S, T, B, slab):
     dec = Decoder(A, pi, algo='tmem')
     p, s = dec.decode_host(E, L, slab_frames=slab)
     assert np.array_equal(p, want_p) and np.array_equal(s, want_s)
+    ps, ss = Decoder(A, pi, algo='stream').decode_host(E, L, slab_frames=slab)      # the streaming kernel resumes too
+    assert np.array_equal(ps, want_p) and np.array_equal(ss, want_s)
     if S <= 384 or S % 2 == 0:
         # the banded kernels resume a frame range too (here on a banded matrix with tie-stress values; S = 722 takes the
         # tensor-memory variant)
@@ -469,3 +471,25 @@ def test_wave_decoder_matches_single_batch_and_oracle(Decoder, algo):
     waves = wd.run(B, fill, sink)
     assert [b - a for a, b in waves] == [5, 5, 5, 5, 3]
     assert np.array_equal(got_p, ref_paths) and np.array_equal(got_s, ref_scores)
+
+
+def test_stream_kernel_many_sub_batches_and_big_state_sets(Decoder):
+    """VIT_ALGO_STREAM: more sub-batches than SMs (the producer runs ahead across sub-batch boundaries), ragged lengths,
+    and state sets past what the tensor-memory kernel's clusters cover."""
+    from viterbi_spl_b200 import _lib
+    for S, B, T in ((33, 14 * 148 + 29, 12), (1100, 5, 9), (722, 40, 33)):
+        A, pi = synth.dyadic_hmm(S, seed=S, coarse=True)
+        E = synth.batch('tie_stress', min(B, 64), T, S, seed0=3 * S)
+        E = np.ascontiguousarray(np.tile(E, ((B + len(E) - 1) // len(E), 1, 1))[:B])
+        L = np.random.default_rng(S).integers(0, T + 1, size=B).astype(np.int32)
+        L[0] = T
+        want_p, want_s = c_oracle.decode_batch_c(A, pi, E, L)
+        p, s = Decoder(A, pi, algo='stream').decode_host(E, L)
+        assert np.array_equal(p, want_p) and np.array_equal(s, want_s), (S, B, T)
+    # auto: a dense 722-state matrix takes the streaming kernel once the batch fills its pass, the tensor-memory kernel
+    # for small batches
+    L_ = _lib.load()
+    assert L_.vit_select_algo(4096, 100, 722) == _lib.ALGO_STREAM
+    assert L_.vit_select_algo(64, 100, 722) == _lib.ALGO_TMEM
+    assert L_.vit_select_algo(4096, 100, 361) == _lib.ALGO_TMEM
+    assert L_.vit_select_algo(8, 10, 1100) == _lib.ALGO_STREAM

@@ -54,7 +54,8 @@ def main():
     logA_T, log_pi = hmm_params.log_params(A, pi, add_tiny=(cfg['model'] != 'imm'))
     algo = a.algo
     if algo == 'dense':
-        algo = 'tmem' if _lib.load().vit_select_algo(1, T, S) == _lib.ALGO_TMEM else 'auto'
+        # the dense kernel auto would take for a batch this size (tmem, or stream for big state sets)
+        algo = {v: k for k, v in _lib.ALGO_NAMES.items()}.get(_lib.load().vit_select_algo(cfg['clips'], T, S), 'auto')
     dec = ViterbiDecoder(logA_T, log_pi, device=dev, algo=algo)
     lo, hi = sharding.shard_bounds(cfg['clips'], rank, world)
     n_mine = hi - lo
@@ -125,7 +126,7 @@ def main():
     job_ms, decode_ms = float(t[0]), float(t[1])
     frames = cfg['clips'] * T
     if rank == 0:
-        cells = S * S if algo in ('tmem', 'cluster', 'backpointer') or dec.structure.kind != 1 else None
+        cells = S * S if algo in ('tmem', 'stream', 'cluster', 'backpointer') or dec.structure.kind != 1 else None
         line = {
             'metric': 'viterbi_frames_per_sec', 'unit': 'frames/s', 'n_gpus': world, 'scaling': 'strong',
             'config': {'workload': f"config {a.config}: {cfg['clips']} clips x {T} frames x {S} states ({cfg['model']} state set)",
@@ -136,7 +137,7 @@ def main():
                        'wave_budget_bytes': wd.budget_bytes},
             'value': frames / (decode_ms * 1e-3), 'decode_ms': decode_ms,
             'job_value_including_generation': frames / (job_ms * 1e-3), 'job_ms': job_ms,
-            'frac_of_fp32_maxplus_peak': (frames * cells / (decode_ms * 1e-3) / (148 * 64 * 1.965e9)) if cells else None,
+            'frac_of_fp32_maxplus_peak': (frames * cells / (decode_ms * 1e-3) / (world * 148 * 64 * 1.965e9)) if cells else None,
             'gpu_launches': _lib.launch_count() - launches0,
             'parity_vs_oracle': checked, 'data': 'synthetic (generated on the device per wave)',
         }

@@ -9,9 +9,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libvit_b200.so')
 
 VIT_OK = 0
-ALGO_AUTO, ALGO_BACKPOINTER, ALGO_CLUSTER, ALGO_TMEM, ALGO_BANDED = 0, 1, 2, 3, 4
+ALGO_AUTO, ALGO_BACKPOINTER, ALGO_CLUSTER, ALGO_TMEM, ALGO_BANDED, ALGO_STREAM = 0, 1, 2, 3, 4, 5
 ALGO_NAMES = {'auto': ALGO_AUTO, 'backpointer': ALGO_BACKPOINTER, 'cluster': ALGO_CLUSTER, 'tmem': ALGO_TMEM,
-              'banded': ALGO_BANDED}
+              'banded': ALGO_BANDED, 'stream': ALGO_STREAM}
 
 # every symbol include/vit_b200.h declares (tests/test_abi.py checks the built library exports them all)
 EXPORTS = ['vit_version', 'vit_strerror', 'vit_last_cuda_error', 'vit_launch_count', 'vit_select_algo',

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libvit_b200.so')
-SOURCES = ['vit_api.cu', 'vit_backpointer.cu', 'vit_cluster.cu', 'vit_tmem.cu', 'vit_fb.cu', 'vit_emis.cu', 'vit_banded.cu', 'vit_banded_wide.cu', 'vit_fb_tc.cu']
+SOURCES = ['vit_api.cu', 'vit_backpointer.cu', 'vit_cluster.cu', 'vit_tmem.cu', 'vit_fb.cu', 'vit_emis.cu', 'vit_banded.cu', 'vit_banded_wide.cu', 'vit_fb_tc.cu', 'vit_stream.cu']
 HEADERS = ['vit_common.cuh', 'vit_tmem.cuh', os.path.join('..', '..', 'include', 'vit_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '--compiler-options', '-fPIC', '-shared', '-Xptxas', '-v']

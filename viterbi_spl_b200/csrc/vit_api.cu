@@ -1,4 +1,5 @@
 // extern "C" surface of libvit_b200.so (declared in include/vit_b200.h).
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -48,6 +49,15 @@ int tmem_decode(const float* logA_T, const float* log_pi, const float* log_emis,
 
 int tmem_clips_in_flight(int S, int* out);
 
+// vit_stream.cu
+bool stream_supported(int S);
+size_t stream_workspace_bytes(int B, int T_max, int S);
+int stream_clips_in_flight(int* out);
+int stream_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
+                  int T_max, int S, void* workspace, size_t workspace_bytes, int64_t* paths, float* scores,
+                  float* delta_out, int t_begin, int t_end, bool do_backtrace, cudaEvent_t ev0, cudaEvent_t ev1,
+                  cudaStream_t stream);
+
 // vit_fb.cu
 size_t fb_workspace_bytes(int B, int T_max, int S);
 bool fb_supported(int S);
@@ -95,13 +105,33 @@ static int check_shape(int B, int T_max, int S) {
   return VIT_OK;
 }
 
-static int resolve_algo(int algo, int S, bool want_bp) {
+// Dense kernel for VIT_ALGO_AUTO.  S <= 384: the tensor-memory kernel (2-CTA clusters, every SM busy; measured 75 % of
+// the FP32 max-plus peak vs 70 % for the streaming kernel at S = 361).  Larger S: the tensor-memory kernel needs
+// clusters of ceil(S / 192) CTAs -- 6 at S = 722, 132 of 148 SMs, 61 % of peak on full passes -- while the streaming
+// kernel runs at 75 % but only with 14 clips on every SM, so the choice depends on how well the batch fills each
+// kernel's pass (B = 0: unknown batch, assume a large one).
+static int auto_dense_algo(int B, int S) {
+  if (tmem_supported(S) && S <= 384) return VIT_ALGO_TMEM;
+  if (stream_supported(S)) {
+    if (!tmem_supported(S)) return VIT_ALGO_STREAM;
+    int qt = 0, qs = 0;
+    if (B > 0 && tmem_clips_in_flight(S, &qt) == VIT_OK && stream_clips_in_flight(&qs) == VIT_OK && qt > 0 && qs > 0) {
+      const double cost_t = (double)((B + qt - 1) / qt) * qt / 0.607;
+      const double cost_s = (double)((B + qs - 1) / qs) * qs / 0.747;
+      return cost_s < cost_t ? VIT_ALGO_STREAM : VIT_ALGO_TMEM;
+    }
+    return VIT_ALGO_STREAM;
+  }
+  return tmem_supported(S) ? VIT_ALGO_TMEM : (cluster_supported(S) ? VIT_ALGO_CLUSTER : VIT_ALGO_BACKPOINTER);
+}
+
+static int resolve_algo(int algo, int S, bool want_bp, int B = 0) {
   if (want_bp) return VIT_ALGO_BACKPOINTER;
-  if (algo == VIT_ALGO_AUTO)
-    return tmem_supported(S) ? VIT_ALGO_TMEM : (cluster_supported(S) ? VIT_ALGO_CLUSTER : VIT_ALGO_BACKPOINTER);
+  if (algo == VIT_ALGO_AUTO) return auto_dense_algo(B, S);
   if (algo == VIT_ALGO_BACKPOINTER) return algo;
   if (algo == VIT_ALGO_CLUSTER) return cluster_supported(S) ? algo : VIT_ERR_UNSUPPORTED_ALGO;
   if (algo == VIT_ALGO_TMEM) return tmem_supported(S) ? algo : VIT_ERR_UNSUPPORTED_ALGO;
+  if (algo == VIT_ALGO_STREAM) return stream_supported(S) ? algo : VIT_ERR_UNSUPPORTED_ALGO;
   return VIT_ERR_INVALID_ARGUMENT;
 }
 
@@ -133,7 +163,7 @@ uint64_t vit_launch_count(void) { return g_launches.load(std::memory_order_relax
 int vit_select_algo(int B, int T_max, int S) {
   int rc = check_shape(B, T_max, S);
   if (rc != VIT_OK) return rc;
-  return resolve_algo(VIT_ALGO_AUTO, S, false);
+  return resolve_algo(VIT_ALGO_AUTO, S, false, B);
 }
 
 int vit_clips_in_flight(int S, int algo, const vit_structure* structure, int* out_clips) {
@@ -146,6 +176,7 @@ int vit_clips_in_flight(int S, int algo, const vit_structure* structure, int* ou
   const int a = resolve_algo(algo, S, false);
   if (a < 0) return a;
   if (a == VIT_ALGO_TMEM) return tmem_clips_in_flight(S, out_clips);
+  if (a == VIT_ALGO_STREAM) return stream_clips_in_flight(out_clips);
   // cluster / backpointer kernels: no fixed quantum worth planning for; one clip per SM is the natural unit
   int num_sms = 148, dev = 0;
   VIT_CUDA_TRY(cudaGetDevice(&dev));
@@ -162,14 +193,18 @@ int vit_workspace_bytes(int B, int T_max, int S, int algo, size_t* out_bytes) {
     *out_bytes = banded_workspace_bytes(B, T_max, S);
     return VIT_OK;
   }
-  int a = resolve_algo(algo, S, false);
+  int a = resolve_algo(algo, S, false, B);
   if (a < 0) return a;
   *out_bytes = (a == VIT_ALGO_TMEM)      ? tmem_workspace_bytes(B, T_max, S)
+               : (a == VIT_ALGO_STREAM)  ? stream_workspace_bytes(B, T_max, S)
                : (a == VIT_ALGO_CLUSTER) ? cluster_workspace_bytes(B, T_max, S)
                                          : bp_workspace_bytes(B, T_max, S, false);
-  // VIT_ALGO_AUTO may resolve to the banded kernels at decode time (opts->structure): cover them as well
+  // VIT_ALGO_AUTO may resolve to the banded kernels at decode time (opts->structure) or to either dense kernel
+  // depending on the batch: cover them all
   if (algo == VIT_ALGO_AUTO) {
-    const size_t b = banded_workspace_bytes(B, T_max, S);
+    size_t b = banded_workspace_bytes(B, T_max, S);
+    if (tmem_supported(S)) b = std::max(b, tmem_workspace_bytes(B, T_max, S));
+    if (stream_supported(S)) b = std::max(b, stream_workspace_bytes(B, T_max, S));
     if (b > *out_bytes) *out_bytes = b;
   }
   return VIT_OK;
@@ -193,7 +228,7 @@ int vit_decode_f32_ex(const float* d_logA_T, const float* d_log_pi, const float*
   else if (algo_req == VIT_ALGO_AUTO && !bp_out && banded_supported(S, structure))
     algo = VIT_ALGO_BANDED;
   else
-    algo = resolve_algo(algo_req, S, bp_out != nullptr);
+    algo = resolve_algo(algo_req, S, bp_out != nullptr, B);
   if (algo < 0) return algo;
   if (!d_workspace) return VIT_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t st = (cudaStream_t)stream;
@@ -211,7 +246,10 @@ int vit_decode_f32_ex(const float* d_logA_T, const float* d_log_pi, const float*
     return tmem_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_paths,
                        d_scores, delta_out, f_begin, f_end, !skip_bt, ev0, ev1, st);
   }
-  if (f_begin != 0 || f_end != T_max || skip_bt) return VIT_ERR_UNSUPPORTED_ALGO;   // frame ranges: tmem / banded only
+  if (algo == VIT_ALGO_STREAM)
+    return stream_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_paths,
+                         d_scores, delta_out, f_begin, f_end, !skip_bt, ev0, ev1, st);
+  if (f_begin != 0 || f_end != T_max || skip_bt) return VIT_ERR_UNSUPPORTED_ALGO;   // frame ranges: tmem / stream / banded only
   if (algo == VIT_ALGO_CLUSTER)
     return cluster_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes,
                           d_paths, d_scores, delta_out, ev0, ev1, st);

@@ -134,7 +134,7 @@ class ViterbiDecoder:
             algo = self.lib.vit_select_algo(1, 1, self.S)      # (auto takes the banded kernel where the matrix allows)
         if algo == _lib.ALGO_BANDED:
             return self.structure.kind == 1
-        return algo == _lib.ALGO_TMEM
+        return algo in (_lib.ALGO_TMEM, _lib.ALGO_STREAM)
 
     def decode_host(self, log_emis, lengths=None, slab_frames=None, out=None):
         """log_emis: host float32 array [B, T, S] (NumPy or CPU tensor).  Copies host->device, decodes, copies the
