@@ -493,3 +493,30 @@ def test_stream_kernel_many_sub_batches_and_big_state_sets(Decoder):
     assert L_.vit_select_algo(64, 100, 722) == _lib.ALGO_TMEM
     assert L_.vit_select_algo(4096, 100, 361) == _lib.ALGO_TMEM
     assert L_.vit_select_algo(8, 10, 1100) == _lib.ALGO_STREAM
+
+
+def test_wave_decoder_single_emission_buffer(Decoder):
+    """When two emission buffers leave less than one quantum per wave, WaveDecoder falls back to one buffer (fill and
+    decode of consecutive waves then serialise on it)."""
+    from viterbi_spl_b200.waves import WaveDecoder, wave_bytes_per_clip
+    A, pi = synth.dyadic_hmm(97, seed=4)
+    B, T, S = 19, 21, 97
+    E = synth.batch('dyadic', B, T, S, seed0=40)
+    want_p, want_s = c_oracle.decode_batch_c(A, pi, E)
+    dec = Decoder(A, pi, algo='tmem')
+    dE = torch.from_numpy(E).cuda()
+    wd = WaveDecoder(dec, T, budget_bytes=5 * wave_bytes_per_clip(T, S, 1))
+    wd.quantum, wd.emission_buffers, wd.bytes_per_clip = 5, 1, wave_bytes_per_clip(T, S, 1)
+    got_p = np.zeros((B, T), np.int64)
+    got_s = np.zeros(B, np.float32)
+
+    def sink(a, b, paths, scores):
+        got_p[a:b] = paths.cpu().numpy()
+        got_s[a:b] = scores.cpu().numpy()
+
+    def fill(a, b, out):
+        out.copy_(dE[a:b])
+
+    waves = wd.run(B, fill, sink)
+    assert [b - a for a, b in waves] == [5, 5, 5, 4] and wd._emis[1] is None
+    assert np.array_equal(got_p, want_p) and np.array_equal(got_s, want_s)

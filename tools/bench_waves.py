@@ -52,13 +52,32 @@ def main():
     T, S = cfg['frames'], cfg['states']
     A, pi = hmm_params.synthetic_hmm(cfg['model'])
     logA_T, log_pi = hmm_params.log_params(A, pi, add_tiny=(cfg['model'] != 'imm'))
-    algo = a.algo
-    if algo == 'dense':
-        # the dense kernel auto would take for a batch this size (tmem, or stream for big state sets)
-        algo = {v: k for k, v in _lib.ALGO_NAMES.items()}.get(_lib.load().vit_select_algo(cfg['clips'], T, S), 'auto')
-    dec = ViterbiDecoder(logA_T, log_pi, device=dev, algo=algo)
     lo, hi = sharding.shard_bounds(cfg['clips'], rank, world)
     n_mine = hi - lo
+    algo = a.algo
+    if algo == 'dense':
+        # the dense kernel for this JOB: for S <= 384 the tensor-memory kernel; for bigger state sets whichever of the
+        # tensor-memory and the streaming kernel needs less time for the wave plan HBM allows (passes x clips per pass /
+        # measured efficiency of a full pass: 0.607 and 0.747 of the FP32 max-plus peak at S = 722)
+        from viterbi_spl_b200.waves import plan_waves, wave_bytes_per_clip
+        names = {v: k for k, v in _lib.ALGO_NAMES.items()}
+        algo = names.get(_lib.load().vit_select_algo(n_mine, T, S), 'auto')
+        if S > 384:
+            free, _ = torch.cuda.mem_get_info()
+            best = None
+            for cand, eff in (('tmem', 0.607), ('stream', 0.747)):
+                try:
+                    qc = _lib.clips_in_flight(S, _lib.ALGO_NAMES[cand])
+                except Exception:
+                    continue
+                nb = 2 if int(free * 0.85) // wave_bytes_per_clip(T, S, 2) >= qc else 1
+                plan = plan_waves(n_mine, wave_bytes_per_clip(T, S, nb), int(free * 0.85), qc)
+                cost = sum(-(-(y - x) // qc) for x, y in plan) * qc / eff
+                if best is None or cost < best[0]:
+                    best = (cost, cand)
+            if best:
+                algo = best[1]
+    dec = ViterbiDecoder(logA_T, log_pi, device=dev, algo=algo)
     wd = WaveDecoder(dec, T, max_wave_clips=a.max_wave_clips)
 
     checked = {'clips': 0, 'equal': None}
@@ -97,10 +116,11 @@ def main():
         torch.cuda.synchronize()
 
     # warm-up: one quantum through the same path (module load, workspace growth is part of the first wave otherwise)
-    warm = WaveDecoder(dec, T, max_wave_clips=wd.quantum)
-    warm.run(min(n_mine, wd.quantum), fill, lambda *x: decode_events[-1].append(None))
+    warm = WaveDecoder(dec, T, max_wave_clips=32)
+    warm.run(min(n_mine, 32), fill, lambda *x: decode_events[-1].append(None))
     del warm
     decode_events.clear()
+    dec._ws = None
     torch.cuda.empty_cache()
     wd = WaveDecoder(dec, T, max_wave_clips=a.max_wave_clips)
 
@@ -134,6 +154,7 @@ def main():
                        'halfwidth': int(dec.structure.halfwidth),
                        'emission_bytes_total': cfg['clips'] * T * S * 4,
                        'waves_rank0': [b - a_ for a_, b in waves], 'wave_quantum': wd.quantum,
+                       'emission_buffers': wd.emission_buffers,
                        'wave_budget_bytes': wd.budget_bytes},
             'value': frames / (decode_ms * 1e-3), 'decode_ms': decode_ms,
             'job_value_including_generation': frames / (job_ms * 1e-3), 'job_ms': job_ms,

@@ -9,7 +9,8 @@ recording per call, dcnet/softmax_viterbi.py:3033-3040): a wave is just a smalle
   busy (``vit_clips_in_flight``: 1036 for the tensor-memory kernel at S = 361, 1184 for the banded kernels) -- so no
   launch ends with a partly filled pass over the SMs (section 8e: "choose sequences-per-CTA so every wave is full");
 * two emission buffers alternate, so wave k+1 is produced (generated on the device, or copied from pinned host memory)
-  on a side stream while wave k is decoded.
+  on a side stream while wave k is decoded -- unless two buffers leave less than one quantum per wave where a single
+  buffer holds one (config 3 on the streaming kernel), in which case a full pass beats an overlapped fill.
 
 Host logic only; the compute is ``ViterbiDecoder.decode_device``.
 """
@@ -67,7 +68,14 @@ class WaveDecoder:
                 free, _total = torch.cuda.mem_get_info()
             budget_bytes = int(free * hbm_fraction)
         self.budget_bytes = int(budget_bytes)
-        self.bytes_per_clip = wave_bytes_per_clip(self.T, S)
+        # two emission buffers (wave k+1 is produced while wave k is decoded) unless that leaves less than one quantum
+        # per wave where a single buffer would hold one: long clips of a big state set (config 3: 29 MB per clip) on
+        # the streaming kernel (2072 clips in flight) -- a full pass beats an overlapped fill
+        self.emission_buffers = 2
+        if (self.budget_bytes // wave_bytes_per_clip(self.T, S, 2) < self.quantum
+                <= self.budget_bytes // wave_bytes_per_clip(self.T, S, 1)):
+            self.emission_buffers = 1
+        self.bytes_per_clip = wave_bytes_per_clip(self.T, S, self.emission_buffers)
         self.max_wave_clips = max_wave_clips
         self._emis = [None, None]
         self._out = [None, None]
@@ -93,14 +101,15 @@ class WaveDecoder:
         with torch.cuda.device(self.dec.device):
             main, side = torch.cuda.current_stream(), self._fill_stream
             biggest = max(b - a for a, b in waves)
-            for slot in range(min(2, len(waves))):
+            nbuf = self.emission_buffers
+            for slot in range(min(nbuf, len(waves))):
                 self._buffers(slot, biggest)
             side.wait_stream(main)
             decoded = [None, None]           # event: the decode that last read emission buffer `slot` has finished
 
             def produce(k):
                 a, b = waves[k]
-                slot = k & 1
+                slot = k % nbuf
                 emis, _, _ = self._buffers(slot, b - a)
                 with torch.cuda.stream(side):
                     if decoded[slot] is not None:
@@ -113,9 +122,9 @@ class WaveDecoder:
             nxt = produce(0)
             for k, (a, b) in enumerate(waves):
                 lengths, ready = nxt
-                if k + 1 < len(waves):
-                    nxt = produce(k + 1)
-                slot = k & 1
+                if nbuf > 1 and k + 1 < len(waves):
+                    nxt = produce(k + 1)                 # into the other buffer, while this wave is decoded
+                slot = k % nbuf
                 emis, paths, scores = self._buffers(slot, b - a)
                 main.wait_event(ready)
                 self.dec.decode_device(emis, lengths, paths, scores)
@@ -123,4 +132,6 @@ class WaveDecoder:
                 ev.record(main)
                 decoded[slot] = ev
                 sink(a, b, paths, scores)
+                if nbuf == 1 and k + 1 < len(waves):
+                    nxt = produce(k + 1)                 # same buffer: ordered after this wave's decode
         return waves
