@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VIT_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+#define VIT_B200_VERSION 101 /* major*10000 + minor*100 + patch */
 
 typedef enum vit_status {
   VIT_OK = 0,
@@ -74,6 +74,9 @@ typedef struct vit_structure {
   int32_t halfwidth;   /* d: apart from dense_index, entries that differ from `background` satisfy |i - j| <= d */
   int32_t dense_index; /* the one state that is a dense source column AND a dense target row (unvoiced), or -1 */
   float background;    /* c = the minimum entry of logA^T (log(tiny) = -87.33655 for the reference's matrices) */
+  float dense_row_max; /* max over i != dense_index of logA^T[dense_index][i] (transitions INTO the dense state from the
+                          others; +inf if there is no dense state): lets the backtrace stay on the dense row without
+                          scanning it */
 } vit_structure;
 
 /* Optional extras for vit_decode_f32_ex (all may be zero/NULL). */

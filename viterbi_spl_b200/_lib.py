@@ -23,7 +23,7 @@ EXPORTS = ['vit_version', 'vit_strerror', 'vit_last_cuda_error', 'vit_launch_cou
 class Structure(ctypes.Structure):
     """struct vit_structure"""
     _fields_ = [('kind', ctypes.c_int32), ('halfwidth', ctypes.c_int32), ('dense_index', ctypes.c_int32),
-                ('background', ctypes.c_float)]
+                ('background', ctypes.c_float), ('dense_row_max', ctypes.c_float)]
 
 
 class DecodeOpts(ctypes.Structure):

@@ -114,8 +114,11 @@ static int auto_dense_algo(int B, int S) {
   if (tmem_supported(S) && S <= 384) return VIT_ALGO_TMEM;
   if (stream_supported(S)) {
     if (!tmem_supported(S)) return VIT_ALGO_STREAM;
-    int qt = 0, qs = 0;
-    if (B > 0 && tmem_clips_in_flight(S, &qt) == VIT_OK && stream_clips_in_flight(&qs) == VIT_OK && qt > 0 && qs > 0) {
+    if (B > 0) {
+      // clips per pass of either kernel: asked from the device where there is one, nominal (148 SMs) otherwise
+      int qt = 0, qs = 0;
+      if (tmem_clips_in_flight(S, &qt) != VIT_OK || qt <= 0) qt = (148 / ((S + 191) / 192)) * 14;
+      if (stream_clips_in_flight(&qs) != VIT_OK || qs <= 0) qs = 148 * 14;
       const double cost_t = (double)((B + qt - 1) / qt) * qt / 0.607;
       const double cost_s = (double)((B + qs - 1) / qs) * qs / 0.747;
       return cost_s < cost_t ? VIT_ALGO_STREAM : VIT_ALGO_TMEM;

@@ -67,7 +67,9 @@ template <int D>
 __global__ void __launch_bounds__(bThreads, 1)
 banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict__ log_pi,
                       const float* __restrict__ log_emis, const int32_t* __restrict__ lengths, int B, int T_max, int S,
-                      int jd, float cbg, float* __restrict__ hist, int t_begin, int t_end, int q) {
+                      int jd, float cbg, float* __restrict__ hist, float* __restrict__ rowmax, int t_begin, int t_end,
+                      int q) {
+  // rowmax [B][T_max]: max_i delta_t[i] per frame, for the structured backtrace (vit_cluster.cu)
   // q: clips per CTA and pass (1..8).  The host spreads a batch evenly (1024 clips = 147 CTAs x 7, not 128 x 8): pipeline
   // cs takes clips [2 cs, 2 cs + 2) of the CTA's q, so the last busy pipeline may hold ONE clip and then runs the
   // one-clip instance of the step (half the cells), and a pipeline past q sits the pass out.
@@ -79,10 +81,11 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
   // the step (measured: the D = 14 instance on a +-12 matrix, 4.80 vs 3.75 ms).  So for D > 12 the last SPL offsets of
   // every target live in TENSOR MEMORY (16 columns of this thread's own lane; idle silicon in a SIMT kernel) and come
   // back once per step with one tcgen05.ld, issued at the top of the step and awaited where the sweep first needs them.
-  constexpr int SPL = D > 12 ? 4 : 0;
+  constexpr int SPL = D > 12 ? 8 : (D == 12 ? 4 : 0);
   constexpr int WR = W - SPL;                        // band offsets kept in registers
   constexpr int M_WAIT = (WR + U0 - 3 + 3) / 4;      // first window float4 with a cell at offset r >= WR
-  constexpr int kTmemColsBanded = 64;                // 3 warp groups x 16 columns, rounded up to a power of two
+  constexpr int NTC = 4 * SPL;                       // TMEM columns per thread (16 or 32)
+  constexpr int kTmemColsBanded = 128;               // 3 warp groups x NTC columns, rounded up to a power of two
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_delta[bCS][2][bCPT][bRowLen];
   __shared__ float s_partM[bCS][2][bTGW][bCPT];
@@ -110,7 +113,7 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
     __syncthreads();
     tc_fence_after();
     // my lane of quadrant warp & 3, 16 columns of warp group warp >> 2 (uniform per warp)
-    taddr = __shfl_sync(0xffffffffu, s_tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 16), 0);
+    taddr = __shfl_sync(0xffffffffu, s_tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * NTC), 0);
   }
 #pragma unroll
   for (int n = 0; n < bNJ; ++n) {
@@ -123,13 +126,16 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
       a[n][r] = (jok && i >= 0 && i < S && i != jd) ? logA_T[(size_t)j * S + i] : -INFINITY;
     }
     if constexpr (SPL > 0) {
-      float hi[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int i = j + WR + k - D;
-        hi[k] = (jok && i >= 0 && i < S && i != jd) ? logA_T[(size_t)j * S + i] : -INFINITY;
+      for (int g4 = 0; g4 < SPL / 4; ++g4) {
+        float hi[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = j + WR + 4 * g4 + k - D;
+          hi[k] = (jok && i >= 0 && i < S && i != jd) ? logA_T[(size_t)j * S + i] : -INFINITY;
+        }
+        tmem_st4(taddr + g4 * 16 + n * 4, make_float4(hi[0], hi[1], hi[2], hi[3]));
       }
-      tmem_st4(taddr + 4 * n, make_float4(hi[0], hi[1], hi[2], hi[3]));
     }
     acol[n] = (jok && jd >= 0) ? logA_T[(size_t)j * S + jd] : -INFINITY;   // dense source column: A[jd -> j]
     arow[n] = (jok && jd >= 0) ? logA_T[(size_t)jd * S + j] : -INFINITY;   // dense target row:    A[j -> jd]
@@ -228,15 +234,19 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
           // the band: my window of delta_{t-1} is NW4 aligned float4s starting at my own targets' slot.  One float4 at
           // a time, applied to every (offset r, target n) cell that reads it: only 4 window values are ever live
           const float4* row4 = reinterpret_cast<const float4*>(prev) + tg;
-          float ah[16];                                      // band offsets WR.. of my 4 targets
+          float ah[NTC > 0 ? NTC : 1];                       // band offsets WR.. of my 4 targets
 #pragma unroll
           for (int m = 0; m < NW4; ++m) {
             const float4 v = row4[m];
             const float wv[4] = {v.x, v.y, v.z, v.w};
             if constexpr (SPL > 0) {
               // (short-lived on purpose: fetched per clip two float4s ahead of the first cell that needs them)
-              if (m == M_WAIT - 2) tmem_ld<16>(taddr, ah);
-              if (m == M_WAIT) tmem_wait_ld<16>(ah);
+              // (each group of 4 offsets is fetched one float4 ahead of the first cell that needs it)
+#pragma unroll
+              for (int g4 = 0; g4 < SPL / 4; ++g4) {
+                if (m == M_WAIT + g4 - 1) tmem_ld<16>(taddr + 16 * g4, ah + 16 * g4);
+                if (m == M_WAIT + g4) tmem_wait_ld<16>(ah + 16 * g4);
+              }
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -244,7 +254,7 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
               for (int n = 0; n < bNJ; ++n) {
                 const int r = 4 * m + k - U0 - n;                    // cell (r, n) reads window element U0 + r + n
                 if (r >= 0 && r < WR) acc[c][n] = fmaxf(acc[c][n], __fadd_rn(wv[k], a[n][r]));
-                else if (r >= WR && r < W) acc[c][n] = fmaxf(acc[c][n], __fadd_rn(wv[k], ah[n * 4 + (r - WR)]));
+                else if (r >= WR && r < W) acc[c][n] = fmaxf(acc[c][n], __fadd_rn(wv[k], ah[((r - WR) >> 2) * 16 + n * 4 + ((r - WR) & 3)]));
               }
           }
           // combine the per-warp partials of step t-1: max_{i != jd} delta_{t-1}[i] and the dense target row's
@@ -253,6 +263,7 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
           const float* pm = &s_partM[cs][buf ^ 1][0][c];
           const float* pdd = &s_partD[cs][buf ^ 1][0][c];
           const float dm = fmaxf(fmaxf(fmaxf(pm[0], pm[bCPT]), pm[2 * bCPT]), xd[c]);
+          if (tgw == 0 && lane == 2 && t - 1 < len[c]) rowmax[(size_t)(seq0 + c0 + c) * T_max + (t - 1)] = dm;
           const float dd = fmaxf(fmaxf(fmaxf(pdd[0], pdd[bCPT]), pdd[2 * bCPT]), __fadd_rn(xd[c], a_dd));
           xdn[c] = jd >= 0 ? __fadd_rn(dd, ed[c]) : -INFINITY;
           const float bg = __fadd_rn(dm, cbg);
@@ -340,8 +351,13 @@ static int banded_template_D(int d) {
 // vit_banded_wide.cu: band entries in tensor memory (S <= 768, d <= 56)
 bool banded_wide_supported(int S, const vit_structure* st);
 int banded_wide_forward(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
-                        int T_max, int S, const vit_structure* st, void* packed_ws, float* hist, int t_begin, int t_end,
-                        cudaStream_t stream);
+                        int T_max, int S, const vit_structure* st, void* packed_ws, float* hist, float* rowmax, int t_begin,
+                        int t_end, cudaStream_t stream);
+// vit_cluster.cu: walk that reads only the band window of the state on the path (falls back to the full row when a
+// background source could win)
+int launch_structured_backtrace(const float* logA_T, const float* hist, const float* rowmax, const int32_t* lengths,
+                                int B, int T_max, int S, const vit_structure* st, int64_t* paths, float* scores,
+                                cudaStream_t stream);
 constexpr size_t kWidePackedBytes = (128 * 512 + 8 * 6 * 128 * 4) * sizeof(float);   // TMEM image + shared-memory band tail
 
 static bool banded_narrow_supported(int S, const vit_structure* st) {
@@ -366,8 +382,11 @@ int banded_clips_in_flight(int* out) {
   return VIT_OK;
 }
 
+static size_t banded_rowmax_bytes(int B, int T_max) { return align_up((size_t)B * T_max * sizeof(float), 256); }
+
 size_t banded_workspace_bytes(int B, int T_max, int S) {
-  return align_up(kWidePackedBytes, 256) + align_up((size_t)B * T_max * S * sizeof(float), 256);   // TMEM image + T1 table
+  // TMEM image of the band, row maxima, T1 table
+  return align_up(kWidePackedBytes, 256) + banded_rowmax_bytes(B, T_max) + align_up((size_t)B * T_max * S * sizeof(float), 256);
 }
 
 int banded_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
@@ -377,19 +396,20 @@ int banded_decode(const float* logA_T, const float* log_pi, const float* log_emi
   if (!banded_supported(S, st)) return VIT_ERR_UNSUPPORTED_ALGO;
   if (t_end > T_max) t_end = T_max;
   if (t_begin < 0 || t_begin > t_end) return VIT_ERR_INVALID_ARGUMENT;
-  if (!delta_out && workspace_bytes < banded_workspace_bytes(B, T_max, S)) return VIT_ERR_WORKSPACE_TOO_SMALL;
+  const size_t head_bytes = align_up(kWidePackedBytes, 256) + banded_rowmax_bytes(B, T_max);
+  if (workspace_bytes < (delta_out ? head_bytes : banded_workspace_bytes(B, T_max, S))) return VIT_ERR_WORKSPACE_TOO_SMALL;
   if (B == 0) return VIT_OK;
-  float* hist = delta_out ? delta_out : (float*)((char*)workspace + align_up(kWidePackedBytes, 256));
+  float* rowmax = (float*)((char*)workspace + align_up(kWidePackedBytes, 256));
+  float* hist = delta_out ? delta_out : (float*)((char*)workspace + head_bytes);
   if (!banded_narrow_supported(S, st)) {
     // wide bands / 722-state sets: band entries in tensor memory
-    if (workspace_bytes < align_up(kWidePackedBytes, 256)) return VIT_ERR_WORKSPACE_TOO_SMALL;
     if (ev0) VIT_CUDA_TRY(cudaEventRecord(ev0, stream));
-    const int rc = banded_wide_forward(logA_T, log_pi, log_emis, lengths, B, T_max, S, st, workspace, hist, t_begin, t_end,
-                                       stream);
+    const int rc = banded_wide_forward(logA_T, log_pi, log_emis, lengths, B, T_max, S, st, workspace, hist, rowmax, t_begin,
+                                       t_end, stream);
     if (rc != VIT_OK) return rc;
     if (ev1) VIT_CUDA_TRY(cudaEventRecord(ev1, stream));
     if (!do_backtrace) return VIT_OK;
-    return launch_hist_backtrace(logA_T, hist, lengths, B, T_max, S, paths, scores, stream);
+    return launch_structured_backtrace(logA_T, hist, rowmax, lengths, B, T_max, S, st, paths, scores, stream);
   }
   const int D = banded_template_D(st->halfwidth);
   int num_sms = 148, dev = 0;
@@ -405,8 +425,8 @@ int banded_decode(const float* logA_T, const float* log_pi, const float* log_emi
 #define VIT_BANDED_CASE(DD)                                                                                          \
   case DD: {                                                                                                         \
     banded_forward_kernel<DD><<<grid, bThreads, 0, stream>>>(logA_T, log_pi, log_emis, lengths, B, T_max, S,         \
-                                                              st->dense_index, st->background, hist, t_begin,       \
-                                                              t_end, q);                                             \
+                                                              st->dense_index, st->background, hist, rowmax,        \
+                                                              t_begin, t_end, q);                                    \
   } break;
   switch (D) {
     VIT_BANDED_CASE(4) VIT_BANDED_CASE(8) VIT_BANDED_CASE(12) VIT_BANDED_CASE(14)
@@ -417,7 +437,7 @@ int banded_decode(const float* logA_T, const float* log_pi, const float* log_emi
   VIT_CUDA_TRY(cudaGetLastError());
   if (ev1) VIT_CUDA_TRY(cudaEventRecord(ev1, stream));
   if (!do_backtrace) return VIT_OK;
-  return launch_hist_backtrace(logA_T, hist, lengths, B, T_max, S, paths, scores, stream);
+  return launch_structured_backtrace(logA_T, hist, rowmax, lengths, B, T_max, S, st, paths, scores, stream);
 }
 
 // Host-side structure analysis (h_logA_T is a HOST pointer).  kind = 1 iff, apart from at most one state that is both
@@ -429,6 +449,7 @@ int analyze_structure(const float* A, int S, vit_structure* out) {
   out->halfwidth = 0;
   out->dense_index = -1;
   out->background = 0.f;
+  out->dense_row_max = INFINITY;
   if (S < 2) return VIT_OK;
   float c = A[0];
   for (size_t x = 0; x < (size_t)S * S; ++x) {
@@ -458,6 +479,13 @@ int analyze_structure(const float* A, int S, vit_structure* out) {
   out->background = c;
   out->halfwidth = d;
   out->dense_index = di;
+  out->dense_row_max = INFINITY;
+  if (di >= 0) {
+    float m = -INFINITY;
+    for (int i = 0; i < S; ++i)
+      if (i != di) m = std::max(m, A[(size_t)di * S + i]);
+    out->dense_row_max = m;
+  }
   out->kind = 1;
   out->kind = (banded_narrow_supported(S, out) || banded_wide_supported(S, out)) ? 1 : 0;
   return VIT_OK;

@@ -83,7 +83,9 @@ template <int D>
 __global__ void __launch_bounds__(wThreads, 1)
 wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ logA_T, const float* __restrict__ log_pi,
                     const float* __restrict__ log_emis, const int32_t* __restrict__ lengths, int B, int T_max, int S,
-                    int jd, float cbg, float* __restrict__ hist, int t_begin, int t_end, int q) {
+                    int jd, float cbg, float* __restrict__ hist, float* __restrict__ rowmax, int t_begin, int t_end,
+                    int q) {
+  // rowmax [B][T_max]: max_i delta_t[i] per frame, for the structured backtrace (vit_cluster.cu)
   // q: clips per CTA and pass (1..8), spread evenly by the host; pipeline cs takes clips [4 cs, 4 cs + 4) of them and
   // runs the 4-, 2- or 1-clip instance of the step (a single recording costs a quarter of the cells of a full pipeline)
   constexpr int W = 2 * D + 1, NCH = (W + 3) / 4;
@@ -216,6 +218,7 @@ wide_forward_kernel(const float* __restrict__ packed, const float* __restrict__ 
           float dm = fmaxf(fmaxf(pm[0], pm[wCPT]), fmaxf(pm[2 * wCPT], pm[3 * wCPT]));
           xd[c] = (jd >= 0) ? __fadd_rn(fmaxf(fmaxf(pdd[0], pdd[wCPT]), fmaxf(pdd[2 * wCPT], pdd[3 * wCPT])), ed_prev[c]) : -INFINITY;
           dm = fmaxf(dm, xd[c]);
+          if (Q == 0 && lane == 1 && t - 1 < len[c]) rowmax[(size_t)(seq0 + c0 + c) * T_max + (t - 1)] = dm;
           if (jd >= 0 && Q == 0 && lane == 0 && t - 1 < len[c] && t - 1 >= t_begin)
             st_global_cs_f32(hist + ((size_t)(seq0 + c0 + c) * T_max + (t - 1)) * S + jd, xd[c]);
           const float bg = __fadd_rn(dm, cbg);       // background term fl(max_i delta_i + c)
@@ -369,8 +372,8 @@ size_t banded_wide_workspace_bytes(int B, int T_max, int S) {
 
 template <int D>
 static int launch_wide(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
-                       int T_max, int S, int jd, float cbg, float* packed, float* hist, int t_begin, int t_end, int grid,
-                       int q, cudaStream_t stream) {
+                       int T_max, int S, int jd, float cbg, float* packed, float* hist, float* rowmax, int t_begin,
+                       int t_end, int grid, int q, cudaStream_t stream) {
   constexpr int W = 2 * D + 1, NCH = (W + 3) / 4;
   constexpr int DP = (D + 1) / 2 * 2, U0 = DP - D, NWIN = U0 + 4 * NCH + wNJ, ROW = (wMaxS + NWIN + 8) & ~1;
   constexpr int NTAIL = NCH > wChunksTmem ? NCH - wChunksTmem : 0;
@@ -380,15 +383,15 @@ static int launch_wide(const float* logA_T, const float* log_pi, const float* lo
   note_launch();
   VIT_CUDA_TRY(cudaFuncSetAttribute(wide_forward_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   wide_forward_kernel<D><<<grid, wThreads, smem, stream>>>(packed, logA_T, log_pi, log_emis, lengths, B, T_max, S, jd, cbg,
-                                                          hist, t_begin, t_end, q);
+                                                          hist, rowmax, t_begin, t_end, q);
   note_launch();
   VIT_CUDA_TRY(cudaGetLastError());
   return VIT_OK;
 }
 
 int banded_wide_forward(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
-                        int T_max, int S, const vit_structure* st, void* packed_ws, float* hist, int t_begin, int t_end,
-                        cudaStream_t stream) {
+                        int T_max, int S, const vit_structure* st, void* packed_ws, float* hist, float* rowmax, int t_begin,
+                        int t_end, cudaStream_t stream) {
   int num_sms = 148, dev = 0;
   VIT_CUDA_TRY(cudaGetDevice(&dev));
   VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -400,10 +403,10 @@ int banded_wide_forward(const float* logA_T, const float* log_pi, const float* l
   const int grid = want < num_sms ? want : num_sms;
   float* packed = (float*)packed_ws;
   switch (wide_template_D(st->halfwidth)) {
-    case 20: return launch_wide<20>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, t_begin, t_end, grid, q, stream);
-    case 28: return launch_wide<28>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, t_begin, t_end, grid, q, stream);
-    case 40: return launch_wide<40>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, t_begin, t_end, grid, q, stream);
-    case 56: return launch_wide<56>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, t_begin, t_end, grid, q, stream);
+    case 20: return launch_wide<20>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, rowmax, t_begin, t_end, grid, q, stream);
+    case 28: return launch_wide<28>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, rowmax, t_begin, t_end, grid, q, stream);
+    case 40: return launch_wide<40>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, rowmax, t_begin, t_end, grid, q, stream);
+    case 56: return launch_wide<56>(logA_T, log_pi, log_emis, lengths, B, T_max, S, st->dense_index, st->background, packed, hist, rowmax, t_begin, t_end, grid, q, stream);
     default: return VIT_ERR_UNSUPPORTED_ALGO;
   }
 }

@@ -305,7 +305,7 @@ __device__ __forceinline__ int bt_step(const float* __restrict__ logA_T, int S, 
     const int i = lane + 32 * k;
     if (i < S) argmax_combine(best, arg, __fadd_rn(d[k], a[k]), i);
   }
-  warp_argmax(best, arg);
+  warp_argmax_redux(best, arg);
   return arg;
 }
 
@@ -351,7 +351,7 @@ backtrace_segments_kernel(const float* __restrict__ logA_T, const float* __restr
     const int i = lane + 32 * k;
     if (i < S) argmax_combine(best, arg, d[k], i);
   }
-  warp_argmax(best, arg);
+  warp_argmax_redux(best, arg);
   if (e == len - 1 && lane == 0 && scores) scores[b] = best;
   int s = arg;
   int64_t mine = 0;                         // lane l keeps states[t] for t % 32 == l until a full line is ready
@@ -402,6 +402,186 @@ backtrace_fixup_kernel(const float* __restrict__ logA_T, const float* __restrict
       --t;
     }
   }
+}
+
+// ---- backtrace for STRUCTURED matrices (vit_banded.cu / vit_banded_wide.cu) ------------------------------------------
+// The dense walk above reads the whole delta row of every frame (1.4 KB at S = 361): 4.4 GB per 1024 x 3000 batch, 23 %
+// of a banded step.  For a matrix with band + dense state + constant background c (vit_structure) and a path state
+// s != dense state, the candidates whose matrix entry differs from c are the band window |i - s| <= d and the dense
+// state; every other source i contributes fl(delta_i + c) <= fl(max_i delta_i + c) (fp32 addition of a constant is
+// monotone).  The forward kernels leave max_i delta_t[i] per frame behind (`rowmax`), so:
+//     best over window + dense state  >  fl(rowmax + c)   ==>   the argmax (first maximum) is among those candidates,
+// found from 2d + 2 loads instead of S; otherwise -- a background source wins or ties -- the step falls back to the full
+// scan.  Path states on the dense row (unvoiced) always take the full scan.  Same result as the dense walk, bit for bit.
+template <int PER>
+__device__ __forceinline__ int bt_step_structured(const float* __restrict__ logA_T, int S, int s,
+                                                  const float* __restrict__ row, float rmax, int dband, int jd, float cbg,
+                                                  float a_dd, float row_max_other, int lane) {
+  if (s != jd) {
+    const float* arow = logA_T + (size_t)s * S;
+    float best = -INFINITY;
+    int arg = 0x7fffffff;
+    const int lo = s - dband, ncand = 2 * dband + 2;                    // window, then one slot for the dense state
+    for (int k = lane; k < ncand; k += 32) {
+      const bool is_dense_slot = k == ncand - 1;
+      const int i = is_dense_slot ? jd : lo + k;
+      // (the dense state inside the window is taken by its own slot only)
+      const bool ok = is_dense_slot ? (jd >= 0) : (i >= 0 && i < S && i != jd);
+      if (ok) argmax_combine(best, arg, __fadd_rn(ld_global_nc_f32(row + i), __ldg(arow + i)), i);
+    }
+    warp_argmax_redux(best, arg);
+    if (best > __fadd_rn(rmax, cbg)) return arg;
+  } else {
+    // on the dense row (unvoiced): staying there wins outright when fl(delta_u + A[u -> u]) beats the bound
+    // fl(max_i delta_i + max_{i != u} A[i -> u]) on every other source -- the usual case inside an unvoiced stretch
+    const float stay = __fadd_rn(ld_global_nc_f32(row + jd), a_dd);
+    if (stay > __fadd_rn(rmax, row_max_other)) return jd;
+  }
+  float d[PER];
+  bt_load_row<PER>(row, S, d, lane);
+  return bt_step<PER>(logA_T, S, s, d, lane);
+}
+
+// pull what the next step is likely to read into L2: the window around the state just found (or, on the dense row, the
+// whole row) of delta_{t-2}, and its row maximum
+// `reach` = how far the path can have moved by the time that row is read: (frames of lookahead + 1) * d
+__device__ __forceinline__ void bt_prefetch_structured(const float* __restrict__ row, const float* __restrict__ rmax_p,
+                                                       int S, int s, int reach, int jd, int lane) {
+  if (s == jd) {
+    if (lane * 32 < S) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + lane * 32));
+  } else {
+    const int i = min(max(s - reach + lane * 32, 0), S - 1);
+    if (lane * 32 <= 2 * reach + 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + i));
+    if (lane == 31 && jd >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + jd));
+  }
+  if (lane == 30) asm volatile("prefetch.global.L2 [%0];" ::"l"(rmax_p));
+}
+
+template <int PER>
+__global__ void __launch_bounds__(32 * kBtWarps)
+backtrace_segments_structured_kernel(const float* __restrict__ logA_T, const float* __restrict__ hist,
+                                     const float* __restrict__ rowmax, const int32_t* __restrict__ lengths, int B,
+                                     int T_max, int S, int nseg_max, int dband, int jd, float cbg, float row_max_other,
+                                     int la, int64_t* __restrict__ paths, float* __restrict__ scores) {
+  const float a_dd = jd >= 0 ? __ldg(logA_T + (size_t)jd * S + jd) : -INFINITY;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int seg = warp / B, b = warp - seg * B;
+  if (seg >= nseg_max) return;
+  const int len = lengths ? lengths[b] : T_max;
+  int64_t* p = paths + (size_t)b * T_max;
+  const int lo = seg * kBtSeg;
+  for (int t = max(lo, len) + lane; t < min(lo + kBtSeg, T_max); t += 32) p[t] = -1;
+  if (len <= 0) {
+    if (seg == 0 && lane == 0 && scores) scores[b] = -INFINITY;
+    return;
+  }
+  if (lo >= len) return;
+  const int e = min(lo + kBtSeg, len) - 1;                            // top frame of this segment
+  const float* h = hist + (size_t)b * T_max * S;
+  const float* rm = rowmax + (size_t)b * T_max;
+
+  int s;
+  {
+    // start state: argmax(T1[e]) (imm/tf_viterbi.py:103 for the last segment; a guess for the others)
+    float d[PER];
+    bt_load_row<PER>(h + (size_t)e * S, S, d, lane);
+    float best = -INFINITY;
+    int arg = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int i = lane + 32 * k;
+      if (i < S) argmax_combine(best, arg, d[k], i);
+    }
+    warp_argmax_redux(best, arg);
+    if (e == len - 1 && lane == 0 && scores) scores[b] = best;
+    s = arg;
+  }
+  int64_t mine = 0;
+  if ((e & 31) == lane) mine = s;
+  if ((e & 31) == 0) { if (lane == 0) p[e] = mine; }
+  for (int t = e; t > lo; --t) {
+    // the row read `la` steps from now, wide enough for wherever the path may be by then
+    if (t - 1 - la >= lo) bt_prefetch_structured(h + (size_t)(t - 1 - la) * S, rm + (t - 1 - la), S, s, (la + 1) * dband, jd, lane);
+    s = bt_step_structured<PER>(logA_T, S, s, h + (size_t)(t - 1) * S, __ldg(rm + (t - 1)), dband, jd, cbg, a_dd, row_max_other, lane);
+    const int tt = t - 1;
+    if ((tt & 31) == lane) mine = s;
+    if ((tt & 31) == 0) {
+      if (tt + lane <= e) p[tt + lane] = mine;
+    }
+  }
+}
+
+template <int PER>
+__global__ void __launch_bounds__(32 * kBtWarps)
+backtrace_fixup_structured_kernel(const float* __restrict__ logA_T, const float* __restrict__ hist,
+                                  const float* __restrict__ rowmax, const int32_t* __restrict__ lengths, int B, int T_max,
+                                  int S, int dband, int jd, float cbg, float row_max_other,
+                                  int64_t* __restrict__ paths) {
+  const float a_dd = jd >= 0 ? __ldg(logA_T + (size_t)jd * S + jd) : -INFINITY;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int len = lengths ? lengths[b] : T_max;
+  if (len <= kBtSeg) return;
+  int64_t* p = paths + (size_t)b * T_max;
+  const float* h = hist + (size_t)b * T_max * S;
+  const float* rm = rowmax + (size_t)b * T_max;
+  const int nseg = (len + kBtSeg - 1) / kBtSeg;
+  for (int k = nseg - 2; k >= 0; --k) {
+    int t = (k + 1) * kBtSeg - 1;                                     // top frame of segment k
+    int s_next = (int)p[t + 1];                                       // final (segment k+1 is already exact)
+    while (t >= 0) {
+      const int s = bt_step_structured<PER>(logA_T, S, s_next, h + (size_t)t * S, __ldg(rm + t), dband, jd, cbg, a_dd, row_max_other, lane);
+      if (s == (int)p[t]) break;                                      // merged: everything below is already exact
+      __syncwarp();
+      if (lane == 0) p[t] = s;
+      __syncwarp();
+      s_next = s;
+      --t;
+    }
+  }
+}
+
+// rowmax [B][T_max]: max_i delta_t[i], written by the banded forward kernels for every frame but a clip's last
+int launch_structured_backtrace(const float* logA_T, const float* hist, const float* rowmax, const int32_t* lengths,
+                                int B, int T_max, int S, const vit_structure* st, int64_t* paths, float* scores,
+                                cudaStream_t stream) {
+  if (cudaStream_t bt = backtrace_stream_override()) {
+    if (bt != stream) {
+      cudaEvent_t ev;
+      VIT_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      VIT_CUDA_TRY(cudaEventRecord(ev, stream));
+      VIT_CUDA_TRY(cudaStreamWaitEvent(bt, ev, 0));
+      VIT_CUDA_TRY(cudaEventDestroy(ev));
+      stream = bt;
+    }
+  }
+  const int nseg_max = (T_max + kBtSeg - 1) / kBtSeg;
+  const long long warps = (long long)B * nseg_max;
+  const dim3 block(kBtWarps * 32);
+  const dim3 grid1((unsigned)((warps + kBtWarps - 1) / kBtWarps)), grid2((B + kBtWarps - 1) / kBtWarps);
+  const char* la_s = getenv("VIT_BT_LOOKAHEAD");            // experiment knob: frames of L2 prefetch lookahead
+  const int la = la_s ? atoi(la_s) : 3;
+#define VIT_LAUNCH_BTS(PER)                                                                                         \
+  do {                                                                                                              \
+    backtrace_segments_structured_kernel<PER><<<grid1, block, 0, stream>>>(                                         \
+        logA_T, hist, rowmax, lengths, B, T_max, S, nseg_max, st->halfwidth, st->dense_index, st->background,        \
+        st->dense_row_max, la, paths, scores);                                                                      \
+    note_launch();                                                                                                  \
+    if (nseg_max > 1) {                                                                                             \
+      backtrace_fixup_structured_kernel<PER><<<grid2, block, 0, stream>>>(                                          \
+          logA_T, hist, rowmax, lengths, B, T_max, S, st->halfwidth, st->dense_index, st->background,               \
+          st->dense_row_max, paths);                                                                                \
+      note_launch();                                                                                                \
+    }                                                                                                               \
+  } while (0)
+  if (S <= 32 * 12) VIT_LAUNCH_BTS(12);
+  else if (S <= 32 * 24) VIT_LAUNCH_BTS(24);
+  else return VIT_ERR_UNSUPPORTED_ALGO;
+#undef VIT_LAUNCH_BTS
+  VIT_CUDA_TRY(cudaGetLastError());
+  return VIT_OK;
 }
 
 // shared with vit_tmem.cu: both forward kernels leave the same fp32 delta history behind

@@ -36,6 +36,18 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
   }
 }
 
+// The same reduction in two instructions (sm_100a): the warp maximum with redux.sync.max.f32, then the lowest index
+// among the lanes that hold it with redux.sync.min.u32.  `==` again decides who holds the maximum (+0 / -0 equal).
+__device__ __forceinline__ void warp_argmax_redux(float& v, int& i) {
+  float m;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+  const unsigned cand = (v == m) ? (unsigned)i : 0xffffffffu;
+  unsigned r;
+  asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(cand));
+  v = m;
+  i = (int)r;
+}
+
 // ---- packed fp32 math (sm_100a): FADD2 and FMNMX3 --------------------------------------------------------------
 // add.rn.f32x2 rounds each lane exactly like add.rn.f32 (two independent IEEE binary32 adds), so it is bit-exact
 // against the reference's np.add; it halves the issue slots and, with operand reuse, the register-file reads.
