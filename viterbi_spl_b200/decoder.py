@@ -179,6 +179,26 @@ class ViterbiDecoder:
             return hp.numpy(), hs.numpy()
         return hp.numpy().copy(), hs.numpy().copy()
 
+    def decode_host_st(self, log_emis_st):
+        """ONE recording given as the reference gives it to its log-domain entry point: host float32 ``[S, T]``
+        (imm/tf_viterbi.py:75-89).  Uploaded as it is and transposed to ``[T, S]`` on the device -- the reference's
+        host-side transposing copy is the most expensive thing left in a single-recording call.  Returns NumPy
+        (path int64 [T], score float32)."""
+        E = torch.as_tensor(log_emis_st)
+        assert E.dtype == torch.float32 and E.ndim == 2 and E.shape[0] == self.S
+        S, T = E.shape
+        with torch.cuda.device(self.device):
+            src = self._pinned_buf('emis_st', (S, T), torch.float32)
+            src.copy_(E)
+            dE = src.to(self.device, non_blocking=True).t().contiguous().view(1, T, S)
+            paths, scores = self.decode_device(dE)
+            hp = self._pinned_buf('paths', (1, T), torch.int64)
+            hs = self._pinned_buf('scores', (1,), torch.float32)
+            hp.copy_(paths, non_blocking=True)
+            hs.copy_(scores, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return hp.numpy()[0].copy(), hs.numpy()[0].copy()
+
     def _decode_host_slabs(self, src, dL, slab):
         """Upload frames [t0, t1) of every clip (one strided 2-D copy per slab) on the copy stream; the compute
         stream runs the recursion over slab k as soon as its copy has landed and while slab k+1 is in flight."""

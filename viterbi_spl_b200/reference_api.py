@@ -21,6 +21,7 @@ D (class)  imm/tf_imm.py:90 ``Viterbi.viterbi_librosa_fn``               ``ImmVi
 =========  ===========================================================  =======================================
 """
 import hashlib
+import zlib
 from collections import OrderedDict
 
 import numpy as np
@@ -33,12 +34,20 @@ _DECODERS = OrderedDict()
 _MAX_CACHED = 8
 
 
+def _content_key(x):
+    """Content fingerprint of a float32 array at close to memory speed: CRC-32 of the bytes plus a digest of the
+    per-row sums of the bit patterns (a cryptographic hash of the 2 MB matrix of a 722-state model costs 4 ms -- as much
+    as decoding a recording)."""
+    x = np.ascontiguousarray(x)
+    rows = x.reshape(x.shape[0], -1).view(np.uint32).sum(axis=1, dtype=np.uint64)
+    return (x.shape, zlib.crc32(memoryview(x).cast('B')), hashlib.blake2b(rows.tobytes(), digest_size=16).digest())
+
+
 def _decoder_for(log_transition_matrix_T, log_prob_init):
     """Device-resident parameters are cached by content so per-call families do not re-upload the matrix."""
     A = np.require(log_transition_matrix_T, np.float32, ['C'])
     pi = np.require(log_prob_init, np.float32, ['C'])
-    key = (A.shape, hashlib.blake2b(A.tobytes(), digest_size=16).digest(),
-           hashlib.blake2b(pi.tobytes(), digest_size=16).digest())
+    key = (_content_key(A), hashlib.blake2b(pi.tobytes(), digest_size=16).digest())
     dec = _DECODERS.get(key)
     if dec is None:
         dec = ViterbiDecoder(A, pi)
@@ -53,9 +62,20 @@ def _decoder_for(log_transition_matrix_T, log_prob_init):
 def _decode_ts(log_transition_matrix_T, log_prob_init, log_probs_ts):
     """[T, S] log emissions -> int64[T] via the GPU decoder."""
     E = np.require(log_probs_ts, np.float32, ['C'])
-    assert not np.any(np.isnan(E)), 'emissions contain NaN'
+    assert not np.isnan(E.min()), 'emissions contain NaN'            # (min propagates NaN: one pass, no temporary)
     paths, _ = _decoder_for(log_transition_matrix_T, log_prob_init).decode_host(E[None])
     return paths[0]
+
+
+def _decode_st(log_transition_matrix_T, log_prob_init, log_probs_st):
+    """[S, T] log emissions, C-contiguous -> int64[T].  The transpose the reference does on the host
+    (imm/tf_viterbi.py:89, a strided copy of the whole table) happens on the GPU after the upload instead."""
+    E = log_probs_st
+    if not E.flags['C_CONTIGUOUS']:
+        return _decode_ts(log_transition_matrix_T, log_prob_init, np.require(E.T, np.float32, ['C']))
+    assert not np.isnan(E.min()), 'emissions contain NaN'
+    paths, _ = _decoder_for(log_transition_matrix_T, log_prob_init).decode_host_st(E)
+    return paths
 
 
 # ---- log-domain (Family D) ----------------------------------------------------------------------------------------
@@ -69,8 +89,7 @@ def viterbi_librosa_fn(*, log_transition_matrix_T, log_prob_init, log_probs_st):
     assert len(log_prob_init) == S
     assert log_probs_st.dtype == np.float32
     assert log_probs_st.shape[0] == S
-    probs = np.require(log_probs_st.T, requirements=['C'])           # :89
-    return _decode_ts(B, log_prob_init, probs)
+    return _decode_st(B, log_prob_init, log_probs_st)                # (:89's transpose runs on the GPU)
 
 
 # ---- Family A: prob-domain in, logs taken on every call -------------------------------------------------------------
