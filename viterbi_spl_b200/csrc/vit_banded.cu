@@ -165,6 +165,10 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
 #pragma unroll
     for (int c = 0; c < CPT; ++c) pe[c] = log_emis + ((size_t)min(seq0 + c0 + c, B - 1) * T_max + t_begin) * S + j0;
     const int t_stop = min(maxlen, t_end);
+    // rowmax index of frame t - 1 is rmi[c] + t (the host keeps B * T_max below 2^31 on this path)
+    int rmi[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) rmi[c] = (seq0 + c0 + c) * T_max - 1;
     float xd[CPT];                                          // delta_{t-1}[jd] of my clips
 #pragma unroll
     for (int c = 0; c < CPT; ++c) xd[c] = -INFINITY;
@@ -263,7 +267,7 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
           const float* pm = &s_partM[cs][buf ^ 1][0][c];
           const float* pdd = &s_partD[cs][buf ^ 1][0][c];
           const float dm = fmaxf(fmaxf(fmaxf(pm[0], pm[bCPT]), pm[2 * bCPT]), xd[c]);
-          if (tgw == 0 && lane == 2 && t - 1 < len[c]) rowmax[(size_t)(seq0 + c0 + c) * T_max + (t - 1)] = dm;
+          if (tgw == 0 && lane == 2 && t - 1 < len[c]) rowmax[rmi[c] + t] = dm;
           const float dd = fmaxf(fmaxf(fmaxf(pdd[0], pdd[bCPT]), pdd[2 * bCPT]), __fadd_rn(xd[c], a_dd));
           xdn[c] = jd >= 0 ? __fadd_rn(dd, ed[c]) : -INFINITY;
           const float bg = __fadd_rn(dm, cbg);
@@ -394,6 +398,7 @@ int banded_decode(const float* logA_T, const float* log_pi, const float* log_emi
                   float* scores, float* delta_out, int t_begin, int t_end, bool do_backtrace, cudaEvent_t ev0,
                   cudaEvent_t ev1, cudaStream_t stream) {
   if (!banded_supported(S, st)) return VIT_ERR_UNSUPPORTED_ALGO;
+  if ((long long)B * T_max >= 0x7fffffffLL) return VIT_ERR_INVALID_ARGUMENT;   // (frame indices are int32 in the kernels)
   if (t_end > T_max) t_end = T_max;
   if (t_begin < 0 || t_begin > t_end) return VIT_ERR_INVALID_ARGUMENT;
   const size_t head_bytes = align_up(kWidePackedBytes, 256) + banded_rowmax_bytes(B, T_max);
