@@ -65,15 +65,18 @@ __device__ __forceinline__ bool is_peak(const float* x, int n, int k, int spw) {
 template <int MODEL, bool SPW5>
 __global__ void __launch_bounds__(32 * kEmisWarps)
 emissions_kernel(const float* __restrict__ logits, const float* __restrict__ prior, long long n_frames, int n_bins, int spw,
-                 float threshold, int out_log, float* __restrict__ out) {
-  extern __shared__ float s_x[];                                     // [kEmisWarps][5][n_bins + 16]: x, m2, m4, peak idx, peak exp
+                 float threshold, int out_log, int pk_cap, float* __restrict__ out) {
+  // per warp: x, m2, m4 rows of n_bins + 16 floats, then the compacted peak list (bin, exp) of pk_cap entries -- peaks
+  // are more than spw bins apart, so pk_cap = n_bins / (spw + 1) + 2 suffices and 5 instead of 3 blocks fit an SM
+  extern __shared__ float s_x[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int np = n_bins + 16;                                        // padded row: 5 + n_bins + 5, rounded up
-  float* x = s_x + (size_t)w * 5 * np + 5;                           // x[k] = logit of bin k; x[-5 .. n+4] valid
-  float* m2 = s_x + (size_t)w * 5 * np + np + 5;
-  float* m4 = s_x + (size_t)w * 5 * np + 2 * np + 5;
-  int* pk_idx = reinterpret_cast<int*>(s_x + (size_t)w * 5 * np + 3 * np);     // compacted peak bins
-  float* pk_e = s_x + (size_t)w * 5 * np + 4 * np;                   // exp(peak logit - max)
+  const int per_warp = 3 * np + 2 * pk_cap;
+  float* x = s_x + (size_t)w * per_warp + 5;                         // x[k] = logit of bin k; x[-5 .. n+4] valid
+  float* m2 = s_x + (size_t)w * per_warp + np + 5;
+  float* m4 = s_x + (size_t)w * per_warp + 2 * np + 5;
+  int* pk_idx = reinterpret_cast<int*>(s_x + (size_t)w * per_warp + 3 * np);   // compacted peak bins
+  float* pk_e = s_x + (size_t)w * per_warp + 3 * np + pk_cap;        // exp(peak logit - max)
   const int n_in = MODEL == 0 ? n_bins + 1 : n_bins;
   const int S = n_bins + 1;
   const float zero_out = out_log ? logf(kTinyF) : 0.f;               // log(0 + tiny) = -87.33655
@@ -291,7 +294,8 @@ int emissions_run(const float* logits, const float* prior, int B, int T, int n_b
   if (n_bins > 1024) return VIT_ERR_UNSUPPORTED_ALGO;                 // 32 peak flags per lane
   if (model != 0 && model != 1) return VIT_ERR_INVALID_ARGUMENT;
   const bool fast = spw == 5 && n_bins >= 7;
-  const size_t smem = (size_t)kEmisWarps * 5 * (n_bins + 16) * sizeof(float);
+  const int pk_cap = (n_bins / (spw + 1) + 2 + 3) & ~3;              // peaks are more than spw bins apart
+  const size_t smem = (size_t)kEmisWarps * (3 * (n_bins + 16) + 2 * pk_cap) * sizeof(float);
   int num_sms = 148, dev = 0;
   VIT_CUDA_TRY(cudaGetDevice(&dev));
   VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -303,7 +307,7 @@ int emissions_run(const float* logits, const float* prior, int B, int T, int n_b
     if (smem > 48 * 1024)                                                                                           \
       VIT_CUDA_TRY(cudaFuncSetAttribute(emissions_kernel<M, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     emissions_kernel<M, F><<<(unsigned)blocks, 32 * kEmisWarps, smem, stream>>>(logits, prior, n_frames, n_bins, spw, \
-                                                                                threshold, out_log, out);          \
+                                                                                threshold, out_log, pk_cap, out);  \
   } while (0)
   if (model == 0) { if (fast) VIT_EMIS_LAUNCH(0, true); else VIT_EMIS_LAUNCH(0, false); }
   else { if (fast) VIT_EMIS_LAUNCH(1, true); else VIT_EMIS_LAUNCH(1, false); }
