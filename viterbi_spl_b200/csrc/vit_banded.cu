@@ -81,11 +81,11 @@ banded_forward_kernel(const float* __restrict__ logA_T, const float* __restrict_
   // the step (measured: the D = 14 instance on a +-12 matrix, 4.80 vs 3.75 ms).  So for D > 12 the last SPL offsets of
   // every target live in TENSOR MEMORY (16 columns of this thread's own lane; idle silicon in a SIMT kernel) and come
   // back once per step with one tcgen05.ld, issued at the top of the step and awaited where the sweep first needs them.
-  constexpr int SPL = D > 12 ? 8 : (D == 12 ? 4 : 0);
+  constexpr int SPL = D > 12 ? 12 : (D == 12 ? 4 : 0);
   constexpr int WR = W - SPL;                        // band offsets kept in registers
   constexpr int M_WAIT = (WR + U0 - 3 + 3) / 4;      // first window float4 with a cell at offset r >= WR
   constexpr int NTC = 4 * SPL;                       // TMEM columns per thread (16 or 32)
-  constexpr int kTmemColsBanded = 128;               // 3 warp groups x NTC columns, rounded up to a power of two
+  constexpr int kTmemColsBanded = 256;               // 3 warp groups x NTC columns, rounded up to a power of two
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_delta[bCS][2][bCPT][bRowLen];
   __shared__ float s_partM[bCS][2][bTGW][bCPT];
