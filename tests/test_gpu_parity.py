@@ -113,6 +113,10 @@ def test_reference_entry_points(Decoder):
     got = api.viterbi_librosa_fn(log_transition_matrix_T=g['logA_T'], log_prob_init=g['log_pi'],
                                  log_probs_st=np.require(g['log_probs_ts'].T, requirements=['C']))
     assert np.array_equal(got, g['states'])
+    # eager-TF twin of the log-domain function (imm/tf_viterbi.py:8): same math, int32 result, any emission layout
+    got = api.tf_viterbi_librosa_fn(tf_log_transition_matrix_T=g['logA_T'], tf_log_prob_init=g['log_pi'],
+                                    tf_or_np_log_probs_st=g['log_probs_ts'].T)
+    assert got.dtype == np.int32 and np.array_equal(got, g['states'])
 
     # Family B (tonet): F-ordered prob-domain [S, T], logged in place
     b = load('tonet_family_b.npz')

@@ -44,6 +44,12 @@ def test_log_domain_entry_point_asserts_like_the_reference():
         api.viterbi_librosa_fn(log_transition_matrix_T=A, log_prob_init=pi[:5], log_probs_st=E)
     with pytest.raises(TypeError):           # keyword-only, like the reference signature
         api.viterbi_librosa_fn(A, pi, E)
+    with pytest.raises(AssertionError):      # imm/tf_viterbi.py:28-29 shape of the emissions
+        api.tf_viterbi_librosa_fn(tf_log_transition_matrix_T=A, tf_log_prob_init=pi, tf_or_np_log_probs_st=E[:5])
+    with pytest.raises(AssertionError):      # :26 len(prob_init)
+        api.tf_viterbi_librosa_fn(tf_log_transition_matrix_T=A, tf_log_prob_init=pi[:5], tf_or_np_log_probs_st=E)
+    with pytest.raises(TypeError):
+        api.tf_viterbi_librosa_fn(A, pi, E)
 
 
 def test_family_a_asserts_like_the_reference():

@@ -14,7 +14,8 @@ A          dcnet/softmax_viterbi.py:2433 ``Viterbi.viterbi_librosa_fn``  ``Viter
            dcnet/tf_viterbi_decoding.py:156 ``viterbi_librosa_c_fn``     ``viterbi_librosa_c_fn``
 numba      dcnet/tf_viterbi_decoding.py:119 ``viterbi_numba_fn``,        ``viterbi_numba_fn``, ``viterbi_numba.core``
            dcnet/aot_viterbi_core.py:8 ``viterbi_numba.core``
-TF         dcnet/tf_viterbi_decoding.py:23 ``viterbi_tf_fn``             ``viterbi_tf_fn`` (NumPy in, int32 out)
+TF         dcnet/tf_viterbi_decoding.py:23 ``viterbi_tf_fn``,            ``viterbi_tf_fn``, ``tf_viterbi_librosa_fn``
+           imm/tf_viterbi.py:8 ``tf_viterbi_librosa_fn``                 (NumPy in, int32 out)
 B          tonet/softmax_priors.py:1841 ``Viterbi.viterbi_librosa_fn``   ``ViterbiB.viterbi_librosa_fn``
 C          dcnet/softmax_viterbi.py:2636 ``SoftMaxViterbi...``           ``SoftMaxViterbi.viterbi_librosa_fn``
 D (class)  imm/tf_imm.py:90 ``Viterbi.viterbi_librosa_fn``               ``ImmViterbi.viterbi_librosa_fn``
@@ -90,6 +91,21 @@ def viterbi_librosa_fn(*, log_transition_matrix_T, log_prob_init, log_probs_st):
     assert log_probs_st.dtype == np.float32
     assert log_probs_st.shape[0] == S
     return _decode_st(B, log_prob_init, log_probs_st)                # (:89's transpose runs on the GPU)
+
+
+def tf_viterbi_librosa_fn(*, tf_log_transition_matrix_T, tf_log_prob_init, tf_or_np_log_probs_st):
+    """imm/tf_viterbi.py:8-72 for NumPy inputs (TensorFlow is not a dependency here): the log-domain decode with the
+    eager-TF argument names, shape asserts of :25-29 and the ``np.int32[T]`` result of :62.  ``tf.argmax`` documents no
+    tie order; first-max-wins (NumPy, a1) is the pinned behaviour."""
+    B = np.asarray(tf_log_transition_matrix_T, np.float32)
+    probs = np.asarray(tf_or_np_log_probs_st, np.float32)            # (:21 convert_to_tensor(..., tf.float32))
+    prob_init = np.asarray(tf_log_prob_init, np.float32)
+    S = len(B)
+    assert B.shape == (S, S)
+    assert len(prob_init) == S
+    T = probs.shape[1]
+    assert probs.shape == (S, T)
+    return _decode_st(np.require(B, np.float32, ['C']), prob_init, probs).astype(np.int32)
 
 
 # ---- Family A: prob-domain in, logs taken on every call -------------------------------------------------------------
