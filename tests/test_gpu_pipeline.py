@@ -56,7 +56,8 @@ def test_shaun_model_matches_tonet_golden_and_full_pipeline(pl):
     assert agree >= 0.99, agree
 
 
-@pytest.mark.parametrize('spw,n_bins', [(5, 64), (16, 100), (20, 721), (1, 3)])
+@pytest.mark.parametrize('spw,n_bins', [(5, 64), (16, 100), (20, 721), (1, 3), (5, 7), (5, 13), (5, 360), (5, 383), (5, 384),
+                                        (5, 385), (5, 6)])
 def test_peak_picking_is_exact_with_ties_and_reflect_padding(pl, spw, n_bins):
     """Quantised logits (many equal neighbours) against the NumPy argmax-of-window rule of
     find_peaks_all_at_once_np_fn (dcnet/softmax_viterbi.py:2508-2528), restated here for arbitrary width."""
@@ -69,6 +70,34 @@ def test_peak_picking_is_exact_with_ties_and_reflect_padding(pl, spw, n_bins):
     assert np.array_equal(p[:, :n_bins] != 0, want)
     none = ~want.any(1)
     assert np.all(p[none, n_bins] == 1)                                     # no peak: E[unvoiced] = 1
+
+
+@pytest.mark.parametrize('model,n_bins,scaled', [('softmax', 360, True), ('softmax', 320, False), ('shaun', 360, False),
+                                                 ('shaun', 37, False), ('softmax', 384, True)])
+def test_register_window_kernel_agrees_with_the_generic_kernel(pl, model, n_bins, scaled, monkeypatch):
+    """spw = 5 takes the register-window kernel (12 bins per lane, cp.async ring, float4 rows at the alignment shift of
+    every frame); VIT_EMIS_GENERIC keeps the generic one.  Same peaks exactly, values within the softmax-sum rounding."""
+    g = torch.Generator(device='cuda'); g.manual_seed(n_bins)
+    n_in = n_bins + 1 if model == 'softmax' else n_bins
+    logits = 2 * torch.randn((3, 41, n_in), device='cuda', generator=g)
+    logits[0, 3] = 0.0                                                      # a flat frame: no voiced peak at all
+    logits[1, 5, n_in - 7:] = 9.0                                           # a plateau running into the reflected edge
+    prior = None
+    if scaled:
+        prior = torch.rand((n_bins + 1,), device='cuda', generator=g) * 0.01 + 1e-3
+    m = pl.SOFTMAX if model == 'softmax' else pl.SHAUN
+    for out_log in (True, False):
+        a = pl.emissions_device(logits, n_bins, m, prior, 5, 0.3, out_log=out_log)
+        monkeypatch.setenv('VIT_EMIS_GENERIC', '1')
+        b = pl.emissions_device(logits, n_bins, m, prior, 5, 0.3, out_log=out_log)
+        monkeypatch.delenv('VIT_EMIS_GENERIC')
+        zero = float(np.log(np.finfo(np.float32).tiny)) if out_log else 0.0
+        assert torch.equal(a == zero, b == zero)
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-4 if out_log else 0.0)
+        # an output table that is not 16-byte aligned cannot take float4 rows: the library falls back by itself
+        flat = torch.empty((a.numel() + 1,), dtype=torch.float32, device='cuda')
+        c = pl.emissions_device(logits, n_bins, m, prior, 5, 0.3, out_log=out_log, out=flat[1:].view(a.shape))
+        assert torch.equal(c, b)
 
 
 def test_voiced_bins_and_batched_pipeline(pl):

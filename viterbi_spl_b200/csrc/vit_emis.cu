@@ -19,6 +19,9 @@
 //
 // HBM-bound byte work: 4 B read + 4 B written per state-frame.  One warp per frame; the frame's logits are staged in
 // shared memory for the +-spw neighbourhood tests; loads and stores are coalesced 128-byte lines.
+#include <cstdint>
+#include <cstdlib>
+
 #include "vit_common.cuh"
 
 namespace vit {
@@ -207,6 +210,176 @@ emissions_kernel(const float* __restrict__ logits, const float* __restrict__ pri
   }
 }
 
+// ---- register-window instance (single_side_peak_width == 5, 7 <= n_bins <= 384, 16-byte aligned output) ------------
+// The instance the reference's models take (dcnet / msnet / ftanet / tonet: spw = 5, 320-721 bins; 360 here).  The
+// generic kernel above spends ~700 instructions per frame, mostly shared-memory round trips (window maxima, peak
+// compaction, row assembly) -- 31 % of HBM bandwidth.  Here a lane owns 12 CONSECUTIVE bins:
+//   * the frame's logits arrive by cp.async (LDGSTS, coalesced 128-byte lines) into a 3-deep ring of rows, two frames
+//     ahead of the one being processed -- no registers, no stall;
+//   * a lane reads its 12 bins + 5 neighbours either side as 7 conflict-free LDS.128 (lane stride 48 B) and does the
+//     whole peak test in registers: pair maxima once, then left / right = one 3-input maximum each;
+//   * peaks are > 5 bins apart, so bins [0,6) and [6,12) of a lane hold at most one each: no compaction, the lane that
+//     finds a peak also evaluates its exp / log;
+//   * the output row is a constant (log(tiny)) except at the peaks: filled in shared memory as float4s, peaks
+//     overwritten, then copied with STG.128 -- the row is staged at the shift (f * S) & 3 so that shared-memory float4s
+//     and 16-byte aligned global float4s coincide (rows of S = 361 floats are not aligned themselves).
+// Same comparisons as emissions_kernel<., true> (exact peaks); the softmax sum is taken in a different order (values
+// differ in the last ulp from either the other kernel or NumPy; tests hold 1e-5 relative).
+constexpr int kRegPer = 12;                          // bins per lane
+constexpr int kRegRow = 400;                         // staged input row: x[k] at index k + 8, k in [-8, 392)
+constexpr int kRegOut = 392;                         // staged output row: shift (< 4) + 385, as float4s
+constexpr int kRegStages = 3;
+constexpr int kRegWarpFloats = kRegStages * kRegRow + kRegOut;
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float warp_max_redux_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(32 * kEmisWarps, 4)
+emissions_reg_kernel(const float* __restrict__ logits, const float* __restrict__ prior, long long n_frames, int n_bins,
+                     float threshold, int out_log, float* __restrict__ out) {
+  extern __shared__ __align__(16) float s_x[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* base = s_x + (size_t)w * kRegWarpFloats;
+  float* orow = base + kRegStages * kRegRow;
+  const int n_in = MODEL == 0 ? n_bins + 1 : n_bins;
+  const int S = n_bins + 1;
+  const float zero_out = out_log ? logf(kTinyF) : 0.f;               // log(0 + tiny) = -87.33655
+  const long long f_stride = (long long)gridDim.x * kEmisWarps;
+  const long long f0 = (long long)blockIdx.x * kEmisWarps + w;
+  for (int i = lane; i < kRegWarpFloats; i += 32) base[i] = 0.f;     // lanes past n_bins read these (results unused)
+  __syncwarp();
+  // frame f -> ring stage st: voiced logits to x[0 .. n_bins), the unvoiced logit (model 0, column 0) to slot 0 of the
+  // row (k = -8: outside every window).  A group is committed even when empty so that the wait count stays uniform.
+  auto fetch = [&](long long f, int st) {
+    if (f < n_frames) {
+      const float* in = logits + f * n_in;
+      const uint32_t dst = smem_u32(base + st * kRegRow + 8);
+#pragma unroll
+      for (int i = 0; i < kRegPer; ++i) {
+        const int k = lane + 32 * i;
+        if (k < n_bins) cp_async4(dst + 4 * k, in + (MODEL == 0 ? 1 : 0) + k);
+      }
+      if (MODEL == 0 && lane == 0) cp_async4(dst - 32, in);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int s = 0; s < kRegStages - 1; ++s) fetch(f0 + s * f_stride, s);
+  int st = 0;
+  for (long long f = f0; f < n_frames; f += f_stride) {
+    {
+      int stn = st + kRegStages - 1;
+      if (stn >= kRegStages) stn -= kRegStages;
+      fetch(f + (kRegStages - 1) * f_stride, stn);
+    }
+    asm volatile("cp.async.wait_group %0;" ::"n"(kRegStages - 1) : "memory");
+    __syncwarp();
+    float* xr = base + st * kRegRow;
+    float* x = xr + 8;
+    if (lane < 5) {                                                  // np.pad(mode='reflect'): -m -> m, n-1+m -> n-1-m
+      x[-1 - lane] = x[1 + lane];
+      x[n_bins + lane] = x[n_bins - 2 - lane];
+    }
+    __syncwarp();
+    // my window: wv[j] = x[12 lane - 8 + j]; bin i of mine is wv[8 + i]; wv[3 .. 24] are used
+    float wv[28];
+    {
+      const float4* w4 = reinterpret_cast<const float4*>(xr) + 3 * lane;
+#pragma unroll
+      for (int m = 0; m < 7; ++m) {
+        const float4 v = w4[m];
+        wv[4 * m] = v.x; wv[4 * m + 1] = v.y; wv[4 * m + 2] = v.z; wv[4 * m + 3] = v.w;
+      }
+    }
+    const float unv_logit = MODEL == 0 ? xr[0] : 0.f;                // column 0 is always a peak (:2521)
+    float m2[24];
+#pragma unroll
+    for (int j = 3; j <= 22; ++j) m2[j] = fmaxf(wv[j], wv[j + 1]);
+    // bin k is a peak iff x[k-5 .. k-1] < x[k] and x[k+1 .. k+5] <= x[k] (first maximum of the window is the centre)
+    float c0 = -INFINITY, c1 = -INFINITY;
+    int i0 = -1, i1 = -1;
+    const int kb = kRegPer * lane;
+#pragma unroll
+    for (int i = 0; i < kRegPer; ++i) {
+      const int q = 8 + i;
+      const float c = wv[q];
+      const float left = fmax3(m2[q - 5], m2[q - 3], wv[q - 1]);
+      const float right = fmax3(m2[q + 1], m2[q + 3], wv[q + 5]);
+      const bool pk = (kb + i < n_bins) && (c > left) && (c >= right);
+      if (i < 6) { if (pk) { c0 = c; i0 = i; } }
+      else { if (pk) { c1 = c; i1 = i; } }
+    }
+    const int n_peaks = __reduce_add_sync(0xffffffffu, (i0 >= 0 ? 1 : 0) + (i1 >= 0 ? 1 : 0));
+    float mx = fmaxf(c0, c1);
+    if (MODEL == 0) mx = fmaxf(mx, unv_logit);
+    mx = warp_max_redux_f32(mx);
+    const float e0 = i0 >= 0 ? expf(c0 - mx) : 0.f;
+    const float e1 = i1 >= 0 ? expf(c1 - mx) : 0.f;
+    float sum = warp_sum(e0 + e1);
+    float unv_out, scale;
+    if (MODEL == 0) {
+      sum += expf(unv_logit - mx);
+      scale = 0.f;
+      const float p0 = prior ? prior[0] : 1.f;
+      unv_out = (n_peaks == 0) ? 1.f / p0 : expf(unv_logit - mx) / sum / p0;      // lone unvoiced peak: 1 / prior (:2560-2563)
+    } else {
+      if (n_peaks == 0) {
+        scale = 0.f;
+        unv_out = 1.f;                                               // no peak: E[unvoiced] = 1 (tonet :1758-1760)
+      } else {
+        const float offset = logf(0.8f / (1.f - 0.8f));
+        const float sg = 2.f * (mx - threshold) + (mx >= threshold ? offset : -offset);   // (:1766-1769)
+        float pv, qv;                                                // expit (:1711-1720)
+        if (sg > 0.f) { const float t = expf(-sg); pv = 1.f / (1.f + t); qv = t / (1.f + t); }
+        else { const float t = expf(sg); pv = t / (1.f + t); qv = 1.f / (1.f + t); }
+        scale = pv / sum;
+        unv_out = qv;
+      }
+    }
+    auto peak_value = [&](float e, int k) {
+      float p;
+      if (MODEL == 0) {
+        p = e / sum;                                                 // np.divide(peak_logits, t) then / priors (:2568-2572)
+        if (prior) p = p / prior[k + 1];
+      } else {
+        p = e * scale;                                               // t = p_voiced / sum; peak_logits * t (:1777-1778)
+      }
+      return out_log ? logf(p + kTinyF) : p;
+    };
+    // output row at shift a: element k of the row sits at orow[a + k], so float4 j of orow is the 16-byte aligned
+    // global float4 j of (out + f * S - a)
+    const int a = (int)((f * S) & 3);
+    const int total = a + S;
+    {
+      const float4 z4 = make_float4(zero_out, zero_out, zero_out, zero_out);
+      for (int j = lane; j < (total + 3) >> 2; j += 32) reinterpret_cast<float4*>(orow)[j] = z4;
+    }
+    __syncwarp();
+    if (i0 >= 0) orow[a + kb + i0] = peak_value(e0, kb + i0);
+    if (i1 >= 0) orow[a + kb + i1] = peak_value(e1, kb + i1);
+    if (lane == 0) orow[a + n_bins] = out_log ? logf(unv_out + kTinyF) : unv_out;
+    __syncwarp();
+    {
+      float* oa = out + f * S - a;                                   // 16-byte aligned
+      const int j1 = total >> 2;
+      for (int j = (a ? 1 : 0) + lane; j < j1; j += 32) reinterpret_cast<float4*>(oa)[j] = reinterpret_cast<const float4*>(orow)[j];
+      if (a && lane >= a && lane < 4) oa[lane] = orow[lane];         // head: the rest of the first float4
+      const int tl = 4 * j1 + lane;
+      if (lane < 4 && tl < total) oa[tl] = orow[tl];                 // tail
+    }
+    __syncwarp();                                                    // orow and the stage are free again
+    if (++st == kRegStages) st = 0;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // states -> (voiced, bins): voiced = s < n_bins; bins = min(s, n_bins - 1); frames past the clip's length (state -1)
 // give voiced = 0, bins = -1.
 __global__ void voiced_bins_kernel(const int64_t* __restrict__ states, long long n, int n_bins, uint8_t* __restrict__ voiced,
@@ -293,12 +466,32 @@ int emissions_run(const float* logits, const float* prior, int B, int T, int n_b
   if (n_frames == 0) return VIT_OK;
   if (n_bins > 1024) return VIT_ERR_UNSUPPORTED_ALGO;                 // 32 peak flags per lane
   if (model != 0 && model != 1) return VIT_ERR_INVALID_ARGUMENT;
-  const bool fast = spw == 5 && n_bins >= 7;
-  const int pk_cap = (n_bins / (spw + 1) + 2 + 3) & ~3;              // peaks are more than spw bins apart
-  const size_t smem = (size_t)kEmisWarps * (3 * (n_bins + 16) + 2 * pk_cap) * sizeof(float);
   int num_sms = 148, dev = 0;
   VIT_CUDA_TRY(cudaGetDevice(&dev));
   VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  const bool no_reg = getenv("VIT_EMIS_GENERIC") != nullptr;         // test / experiment knob: keep the generic kernel
+  if (spw == 5 && n_bins >= 7 && n_bins <= 32 * kRegPer && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && !no_reg) {
+    // the reference's configuration: register-window kernel, 4 blocks of 8 warps per SM
+    const size_t smem = (size_t)kEmisWarps * kRegWarpFloats * sizeof(float);
+    long long blocks = (n_frames + kEmisWarps - 1) / kEmisWarps;
+    const long long cap = (long long)num_sms * 4;
+    if (blocks > cap) blocks = cap;
+    if (model == 0) {
+      VIT_CUDA_TRY(cudaFuncSetAttribute(emissions_reg_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      emissions_reg_kernel<0><<<(unsigned)blocks, 32 * kEmisWarps, smem, stream>>>(logits, prior, n_frames, n_bins, threshold,
+                                                                                  out_log, out);
+    } else {
+      VIT_CUDA_TRY(cudaFuncSetAttribute(emissions_reg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      emissions_reg_kernel<1><<<(unsigned)blocks, 32 * kEmisWarps, smem, stream>>>(logits, prior, n_frames, n_bins, threshold,
+                                                                                  out_log, out);
+    }
+    note_launch();
+    VIT_CUDA_TRY(cudaGetLastError());
+    return VIT_OK;
+  }
+  const bool fast = spw == 5 && n_bins >= 7;
+  const int pk_cap = (n_bins / (spw + 1) + 2 + 3) & ~3;              // peaks are more than spw bins apart
+  const size_t smem = (size_t)kEmisWarps * (3 * (n_bins + 16) + 2 * pk_cap) * sizeof(float);
   long long blocks = (n_frames + kEmisWarps - 1) / kEmisWarps;
   const long long cap = (long long)num_sms * 8;                      // grid-stride: a multiple of the SM count
   if (blocks > cap) blocks = cap;
