@@ -255,29 +255,48 @@ emissions_reg_kernel(const float* __restrict__ logits, const float* __restrict__
   const long long f0 = (long long)blockIdx.x * kEmisWarps + w;
   for (int i = lane; i < kRegWarpFloats; i += 32) base[i] = 0.f;     // lanes past n_bins read these (results unused)
   __syncwarp();
-  // frame f -> ring stage st: voiced logits to x[0 .. n_bins), the unvoiced logit (model 0, column 0) to slot 0 of the
+  // frame -> ring stage st: voiced logits to x[0 .. n_bins), the unvoiced logit (model 0, column 0) to slot 0 of the
   // row (k = -8: outside every window).  A group is committed even when empty so that the wait count stays uniform.
-  auto fetch = [&](long long f, int st) {
-    if (f < n_frames) {
-      const float* in = logits + f * n_in;
-      const uint32_t dst = smem_u32(base + st * kRegRow + 8);
+  // Running pointers (one 64-bit add per frame); rows 0 .. n_full-1 of the 12 need no bound check.
+  const int n_full = n_bins >> 5;
+  const size_t in_step = (size_t)f_stride * n_in;
+  const float* in_fetch = logits + f0 * n_in + (MODEL == 0 ? 1 : 0) + lane;    // my first voiced logit of the next frame to fetch
+  long long f_fetch = f0;
+  auto fetch = [&](int st) {
+    if (f_fetch < n_frames) {
+      const uint32_t dst = smem_u32(base + st * kRegRow + 8 + lane);
+      if (n_full >= kRegPer - 1) {                                   // 352 <= n_bins: the reference's 360-bin models
 #pragma unroll
-      for (int i = 0; i < kRegPer; ++i) {
-        const int k = lane + 32 * i;
-        if (k < n_bins) cp_async4(dst + 4 * k, in + (MODEL == 0 ? 1 : 0) + k);
+        for (int i = 0; i < kRegPer - 1; ++i) cp_async4(dst + 128 * i, in_fetch + 32 * i);
+        if (lane + 32 * (kRegPer - 1) < n_bins) cp_async4(dst + 128 * (kRegPer - 1), in_fetch + 32 * (kRegPer - 1));
+      } else {
+#pragma unroll
+        for (int i = 0; i < kRegPer; ++i)
+          if (lane + 32 * i < n_bins) cp_async4(dst + 128 * i, in_fetch + 32 * i);
       }
-      if (MODEL == 0 && lane == 0) cp_async4(dst - 32, in);
+      if (MODEL == 0 && lane == 0) cp_async4(dst - 32, in_fetch - 1);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    in_fetch += in_step;
+    f_fetch += f_stride;
   };
 #pragma unroll
-  for (int s = 0; s < kRegStages - 1; ++s) fetch(f0 + s * f_stride, s);
+  for (int s = 0; s < kRegStages - 1; ++s) fetch(s);
   int st = 0;
+  // alignment shift of the frame's output row, (f * S) & 3, kept incrementally
+  int a = (int)((f0 * S) & 3);
+  const int a_step = (int)((f_stride * S) & 3);
+  float* o_f = out + f0 * S;
+  const size_t out_step = (size_t)f_stride * S;
+  const int kb = kRegPer * lane;
+  // the unvoiced state is evaluated in the second slot of lane 31 (bins 378 .. 383: never a peak when n_bins <= 378)
+  const bool unv_in_slot = n_bins <= 32 * kRegPer - 6;
+  const float prior0 = (MODEL == 0 && prior) ? prior[0] : 1.f;
   for (long long f = f0; f < n_frames; f += f_stride) {
     {
       int stn = st + kRegStages - 1;
       if (stn >= kRegStages) stn -= kRegStages;
-      fetch(f + (kRegStages - 1) * f_stride, stn);
+      fetch(stn);
     }
     asm volatile("cp.async.wait_group %0;" ::"n"(kRegStages - 1) : "memory");
     __syncwarp();
@@ -305,7 +324,6 @@ emissions_reg_kernel(const float* __restrict__ logits, const float* __restrict__
     // bin k is a peak iff x[k-5 .. k-1] < x[k] and x[k+1 .. k+5] <= x[k] (first maximum of the window is the centre)
     float c0 = -INFINITY, c1 = -INFINITY;
     int i0 = -1, i1 = -1;
-    const int kb = kRegPer * lane;
 #pragma unroll
     for (int i = 0; i < kRegPer; ++i) {
       const int q = 8 + i;
@@ -313,69 +331,83 @@ emissions_reg_kernel(const float* __restrict__ logits, const float* __restrict__
       const float left = fmax3(m2[q - 5], m2[q - 3], wv[q - 1]);
       const float right = fmax3(m2[q + 1], m2[q + 3], wv[q + 5]);
       const bool pk = (kb + i < n_bins) && (c > left) && (c >= right);
-      if (i < 6) { if (pk) { c0 = c; i0 = i; } }
-      else { if (pk) { c1 = c; i1 = i; } }
+      if (i < 6) { c0 = pk ? c : c0; i0 = pk ? i : i0; }
+      else { c1 = pk ? c : c1; i1 = pk ? i : i1; }
     }
-    const int n_peaks = __reduce_add_sync(0xffffffffu, (i0 >= 0 ? 1 : 0) + (i1 >= 0 ? 1 : 0));
+    const bool v0 = i0 >= 0, v1 = i1 >= 0;
+    const int n_peaks = __reduce_add_sync(0xffffffffu, (v0 ? 1 : 0) + (v1 ? 1 : 0));
     float mx = fmaxf(c0, c1);
     if (MODEL == 0) mx = fmaxf(mx, unv_logit);
     mx = warp_max_redux_f32(mx);
-    const float e0 = i0 >= 0 ? expf(c0 - mx) : 0.f;
-    const float e1 = i1 >= 0 ? expf(c1 - mx) : 0.f;
+    const float e0 = v0 ? expf(c0 - mx) : 0.f;
+    const float e1 = v1 ? expf(c1 - mx) : 0.f;
     float sum = warp_sum(e0 + e1);
-    float unv_out, scale;
+    // value of a voiced peak = e * scale (/ prior); p_unv = the unvoiced state's value
+    float scale, p_unv;
     if (MODEL == 0) {
-      sum += expf(unv_logit - mx);
-      scale = 0.f;
-      const float p0 = prior ? prior[0] : 1.f;
-      unv_out = (n_peaks == 0) ? 1.f / p0 : expf(unv_logit - mx) / sum / p0;      // lone unvoiced peak: 1 / prior (:2560-2563)
+      // softmax over the peaks and column 0; a lone unvoiced peak gives e = sum = 1: 1 / prior (:2560-2563)
+      const float eu = expf(unv_logit - mx);
+      sum += eu;
+      scale = __fdividef(1.f, sum);                                  // np.divide(peak_logits, t) (:2568)
+      p_unv = __fdividef(eu * scale, prior0);
     } else {
       if (n_peaks == 0) {
         scale = 0.f;
-        unv_out = 1.f;                                               // no peak: E[unvoiced] = 1 (tonet :1758-1760)
+        p_unv = 1.f;                                                 // no peak: E[unvoiced] = 1 (tonet :1758-1760)
       } else {
         const float offset = logf(0.8f / (1.f - 0.8f));
         const float sg = 2.f * (mx - threshold) + (mx >= threshold ? offset : -offset);   // (:1766-1769)
         float pv, qv;                                                // expit (:1711-1720)
         if (sg > 0.f) { const float t = expf(-sg); pv = 1.f / (1.f + t); qv = t / (1.f + t); }
         else { const float t = expf(sg); pv = t / (1.f + t); qv = 1.f / (1.f + t); }
-        scale = pv / sum;
-        unv_out = qv;
+        scale = __fdividef(pv, sum);                                 // t = p_voiced / sum; peak_logits * t (:1777-1778)
+        p_unv = qv;
       }
     }
-    auto peak_value = [&](float e, int k) {
-      float p;
-      if (MODEL == 0) {
-        p = e / sum;                                                 // np.divide(peak_logits, t) then / priors (:2568-2572)
-        if (prior) p = p / prior[k + 1];
-      } else {
-        p = e * scale;                                               // t = p_voiced / sum; peak_logits * t (:1777-1778)
-      }
-      return out_log ? logf(p + kTinyF) : p;
-    };
+    // two value slots per lane, evaluated without divergence: my peak in bins [0,6), my peak in bins [6,12) -- or, on
+    // lane 31, the unvoiced state
+    const bool s1_unv = unv_in_slot && lane == 31;
+    float p0v = e0 * scale, p1v = e1 * scale;
+    if (MODEL == 0 && prior) {                                       // then / priors (:2571-2572)
+      p0v = __fdividef(p0v, prior[v0 ? kb + i0 + 1 : 0]);
+      p1v = __fdividef(p1v, prior[v1 ? kb + i1 + 1 : 0]);
+    }
+    if (s1_unv) p1v = p_unv;
+    if (out_log) {
+      p0v = logf(p0v + kTinyF);
+      p1v = logf(p1v + kTinyF);
+    }
     // output row at shift a: element k of the row sits at orow[a + k], so float4 j of orow is the 16-byte aligned
     // global float4 j of (out + f * S - a)
-    const int a = (int)((f * S) & 3);
     const int total = a + S;
     {
       const float4 z4 = make_float4(zero_out, zero_out, zero_out, zero_out);
-      for (int j = lane; j < (total + 3) >> 2; j += 32) reinterpret_cast<float4*>(orow)[j] = z4;
+      const int n4 = (total + 3) >> 2;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (lane + 32 * i < n4) reinterpret_cast<float4*>(orow)[lane + 32 * i] = z4;
     }
     __syncwarp();
-    if (i0 >= 0) orow[a + kb + i0] = peak_value(e0, kb + i0);
-    if (i1 >= 0) orow[a + kb + i1] = peak_value(e1, kb + i1);
-    if (lane == 0) orow[a + n_bins] = out_log ? logf(unv_out + kTinyF) : unv_out;
+    if (v0) orow[a + kb + i0] = p0v;
+    if (v1 || s1_unv) orow[a + (s1_unv ? n_bins : kb + i1)] = p1v;
+    if (!unv_in_slot && lane == 0) orow[a + n_bins] = out_log ? logf(p_unv + kTinyF) : p_unv;
     __syncwarp();
     {
-      float* oa = out + f * S - a;                                   // 16-byte aligned
-      const int j1 = total >> 2;
-      for (int j = (a ? 1 : 0) + lane; j < j1; j += 32) reinterpret_cast<float4*>(oa)[j] = reinterpret_cast<const float4*>(orow)[j];
+      float* oa = o_f - a;                                           // 16-byte aligned
+      const int j0 = a ? 1 : 0, j1 = total >> 2;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = lane + 32 * i;
+        if (j >= j0 && j < j1) reinterpret_cast<float4*>(oa)[j] = reinterpret_cast<const float4*>(orow)[j];
+      }
       if (a && lane >= a && lane < 4) oa[lane] = orow[lane];         // head: the rest of the first float4
       const int tl = 4 * j1 + lane;
       if (lane < 4 && tl < total) oa[tl] = orow[tl];                 // tail
     }
     __syncwarp();                                                    // orow and the stage are free again
     if (++st == kRegStages) st = 0;
+    a = (a + a_step) & 3;
+    o_f += out_step;
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
