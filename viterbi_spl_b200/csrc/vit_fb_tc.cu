@@ -2,20 +2,22 @@
 //
 // Same recursion and the same deferred-normaliser scheme as vit_fb.cu (oracle/fb_oracle.py states the semantics; there
 // is no reference implementation: parity unpinned).  Per step the matrix-vector products of all clips of a cluster are
-// ONE small GEMM  D[128 x 32] = M_shard[128 x K] . V[K x 32]:
+// ONE small GEMM  D[128 x 64] = M_shard[128 x K] . [V_hi | V_lo][K x 64]  (32 clips, two bf16 terms of V side by side):
 //   * M_shard  = this CTA's <= 127 rows of A^T (forward) / A (backward), all K source positions, resident in TENSOR
 //                MEMORY for the whole kernel as the A operand of the "TS" form of tcgen05.mma.  fp32 does not fit and
 //                TF32's 10-bit mantissa cannot hold 1e-4 on gamma, so every fp32 value x is split into two bf16 terms
-//                x = hi + lo (16 mantissa bits); four MMAs per K block -- hi.hi, hi.lo, lo.hi, lo.lo -- accumulate in fp32.
+//                x = hi + lo (16 mantissa bits); two N = 64 MMAs per K block -- A_hi . [V_hi | V_lo] and A_lo . [V_hi | V_lo],
+//                i.e. the four products hi.hi, hi.lo, lo.hi, lo.lo -- accumulate in fp32; the epilogue adds the halves.
 //                Row 127 of the forward operand is all ones: D[127][n] = sum_k alpha~[k][n] is the normaliser c_{t-1}
 //                for free.
 //   * V        = alpha~_{t-1} (forward) / w_{t+1} (backward) of 32 clips, bf16 hi and lo copies in shared memory in the
-//                canonical no-swizzle MN-major layout (8 x 16-byte core matrices; validated by tools/microbench_umma.cu),
+//                canonical no-swizzle MN-major layout (8 x 16-byte core matrices; validated by tools/microbench_umma.cu;
+//                per group of 8 K positions: 4 cores of hi, then 4 cores of lo = one N = 64 operand),
 //                double buffered.  Each CTA writes the rows of its own states and pushes them to its peers with bulk
 //                async DSMEM copies that complete on the receiver's mbarrier.
 //   * D        = fp32 in TMEM; 256 threads (two per row = state, 16 clips each) read their row with tcgen05.ld, scale
 //                by 1/c, multiply by the emission likelihoods, store alpha~ / gamma, and write the next V.
-// One thread issues the 96 UTCHMMA of a step and commits them to an mbarrier; the step is a dependency chain
+// One thread issues the 48 UTCHMMA of a step and commits them to an mbarrier; the step is a dependency chain
 // (wait V -> MMA -> epilogue -> exchange), so the tensor pipe is lightly used -- the point is the ~4x shorter chain than
 // the FFMA kernel's, not tensor throughput.
 #include <cstdlib>
@@ -25,7 +27,8 @@
 
 namespace vit {
 
-constexpr int cN = 32;            // clips per cluster (N of the MMA)
+constexpr int cN = 32;            // clips per cluster
+constexpr int cNN = 2 * cN;       // N of the MMA: the bf16 hi copy of V in columns [0, 32), the lo copy in [32, 64)
 constexpr int cM = 128;           // rows of the MMA = TMEM lanes = threads
 constexpr int cThreads = 256;        // two threads per row: thread (m, half) handles clips [16 half, 16 half + 16)
 constexpr int cH = cN / 2;           // clips per thread
@@ -48,7 +51,7 @@ static bool make_tc_plan(int S, TcPlan* p) {
   const int ncmax = p->base + (p->rem ? 1 : 0);
   p->NCP = (ncmax + 15) / 16 * 16;
   p->KP = C * p->NCP;
-  if (p->KP + cN > cTmemCols) return false;               // A hi + lo = KP columns, D = 32 columns
+  if (p->KP + cNN > cTmemCols) return false;              // A hi + lo = KP columns, D = 64 columns
   const size_t smem = (size_t)2 * 2 * p->KP * cN * 2 + 256;
   return smem <= 200 * 1024;
 }
@@ -130,10 +133,10 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
   // dev: timing experiments only (results invalid): 1 = no HBM traffic, 2 = no exchange, 4 = no MMAs
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int KP = p.KP, NCP = p.NCP;
-  const uint32_t LBO = (cN / 8) * 128;                  // bytes between groups of 8 K positions
-  const uint32_t term_bytes = (uint32_t)KP * cN * 2;    // one bf16 copy of V
-  const uint32_t buf_bytes = 2 * term_bytes;            // hi + lo
-  uint8_t* sV = smem_raw;                               // [2 buffers][2 terms][KP/8][4 cores][8 k][8 n] bf16
+  const uint32_t LBO = (cNN / 8) * 128;                 // bytes between groups of 8 K positions
+  const uint32_t lo_off = (cN / 8) * 128;               // the lo copy's cores follow the hi copy's within a K group
+  const uint32_t buf_bytes = (uint32_t)KP * cNN * 2;    // hi + lo
+  uint8_t* sV = smem_raw;                               // [2 buffers][KP/8][8 cores: 4 hi, 4 lo][8 k][8 n] bf16
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * buf_bytes);     // [0..1] V ready, [2] MMA done
   __shared__ float s_c[2][cN];                          // 1 / normalisers of the step (forward: from D row 127)
   __shared__ float s_craw[cN];
@@ -185,33 +188,31 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (C > 1) cluster_sync();
 
-  const uint32_t d_tmem = tbase + KP;                    // accumulator columns [KP, KP + 32)
+  const uint32_t d_tmem = tbase + KP;                    // accumulator columns [KP, KP + 64): M.V_hi | M.V_lo
   // instruction descriptor: D = F32, A = B = BF16, A K-major (TMEM), B MN-major, N >> 3, M >> 4
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(cN >> 3) << 17) | ((uint32_t)(cM >> 4) << 24);
-  const uint32_t slice_bytes = (uint32_t)NCP * cN * 2;   // my rows of one bf16 copy: contiguous in the canonical layout
-  const uint32_t tx_bytes = (C - 1) * 2 * slice_bytes;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(cNN >> 3) << 17) | ((uint32_t)(cM >> 4) << 24);
+  const uint32_t slice_bytes = (uint32_t)NCP * cNN * 2;  // my rows of V (hi and lo cores): contiguous in the canonical layout
+  const uint32_t tx_bytes = (C - 1) * slice_bytes;
   const long long gamma_delta = reinterpret_cast<const char*>(gamma) - reinterpret_cast<const char*>(lik);
 
-  // tcgen05.mma over K blocks [kb0, kb1) of V buffer `vbuf`: four bf16 products per block (hi.hi, hi.lo, lo.hi, lo.lo;
-  // without lo.lo the gamma error reaches 1.03e-4, measured).  Descriptor = start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 |
-  // version 1 << 46; a K block of 16 advances the start field by 2 LBO >> 4 (the smem window is < 256 KB: no carry).
+  // tcgen05.mma over K blocks [kb0, kb1) of V buffer `vbuf`.  All four bf16 products are needed (hi.hi, hi.lo, lo.hi,
+  // lo.lo; without lo.lo the gamma error reaches 1.03e-4, measured), but the hi and lo copies of V sit side by side as
+  // ONE N = 64 operand, so a K block is two MMAs -- A_hi . [V_hi | V_lo] and A_lo . [V_hi | V_lo] -- instead of four
+  // N = 32 ones (the MMAs of a step are issue-latency bound: ~45 clocks each whatever N), and the epilogue adds the two
+  // halves of D.  Descriptor = start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46; a K block of 16 advances
+  // the start field by 2 LBO >> 4 (the smem window is < 256 KB: no carry).
   auto issue_mma = [&](uint32_t vbuf, int kb0, int kb1, uint32_t acc) {
     const uint32_t vb = smem_u32(sV) + vbuf * buf_bytes;
     const uint32_t desc_hi32 = (128u >> 4) | (1u << 14);
-    uint32_t lo_hi = (((vb >> 4) & 0x3FFF) | (((LBO >> 4) & 0x3FFF) << 16)) + kb0 * ((2 * LBO) >> 4);
-    uint32_t lo_lo = ((((vb + term_bytes) >> 4) & 0x3FFF) | (((LBO >> 4) & 0x3FFF) << 16)) + kb0 * ((2 * LBO) >> 4);
+    uint32_t lo = (((vb >> 4) & 0x3FFF) | (((LBO >> 4) & 0x3FFF) << 16)) + kb0 * ((2 * LBO) >> 4);
     uint32_t a_hi = tbase + kb0 * 8, a_lo = tbase + KP / 2 + kb0 * 8;
 #pragma unroll 4
     for (int kb = kb0; kb < kb1; ++kb) {
-      const uint64_t desc_hi = ((uint64_t)desc_hi32 << 32) | lo_hi;
-      const uint64_t desc_lo = ((uint64_t)desc_hi32 << 32) | lo_lo;
-      tc_mma(d_tmem, a_hi, desc_hi, idesc, acc);
+      const uint64_t desc = ((uint64_t)desc_hi32 << 32) | lo;
+      tc_mma(d_tmem, a_hi, desc, idesc, acc);
       acc = 1;
-      tc_mma(d_tmem, a_hi, desc_lo, idesc, 1);
-      tc_mma(d_tmem, a_lo, desc_hi, idesc, 1);
-      tc_mma(d_tmem, a_lo, desc_lo, idesc, 1);
-      lo_hi += (2 * LBO) >> 4;
-      lo_lo += (2 * LBO) >> 4;
+      tc_mma(d_tmem, a_lo, desc, idesc, 1);
+      lo += (2 * LBO) >> 4;
       a_hi += 8;
       a_lo += 8;
     }
@@ -271,7 +272,14 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
         }
         if (!(dev & 4)) { mbar_wait_cta(smem_u32(&s_bar[2]), n_mma & 1u); ++n_mma; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tc_ld16(tlane + KP + n0, d);
+        {
+          // D[:, 0:32] = M . V_hi, D[:, 32:64] = M . V_lo: my 16 clips of both halves
+          float dl[cH];
+          tc_ld16(tlane + KP + n0, d);
+          tc_ld16(tlane + KP + cN + n0, dl);
+#pragma unroll
+          for (int n = 0; n < cH; ++n) d[n] += dl[n];
+        }
         if (!BWD && (warp & 3) == 3) {
           // row 127 = the ones row: c_{t-1}[n].  Lane 31 of warps 3 and 7 holds 16 sums each; the warp turns them into
           // 1 / c and one CTA per cluster records them
@@ -324,7 +332,7 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
           uint4 hi, lo;
           split8(v + 8 * c8, hi, lo);
           *reinterpret_cast<uint4*>(vrow + c8 * 128) = hi;
-          *reinterpret_cast<uint4*>(vrow + term_bytes + c8 * 128) = lo;
+          *reinterpret_cast<uint4*>(vrow + lo_off + c8 * 128) = lo;
         }
       }
       first = false;
@@ -338,9 +346,9 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
       }
       if (C > 1 && !(dev & 2)) {
         if (tid == 0) mbar_arrive_expect_tx(smem_u32(&s_bar[nxt]), tx_bytes);
-        if (tid < (int)(C - 1) * 2) {
-          const uint32_t peer = (rank + 1 + tid / 2) % C;
-          const uint32_t src = smem_u32(sV + nxt * buf_bytes + (tid & 1) * term_bytes + (size_t)rank * slice_bytes);
+        if (tid < (int)(C - 1)) {
+          const uint32_t peer = (rank + 1 + tid) % C;
+          const uint32_t src = smem_u32(sV + nxt * buf_bytes + (size_t)rank * slice_bytes);
           dsmem_bulk_copy(mapa(src, peer), src, slice_bytes, mapa(smem_u32(&s_bar[nxt]), peer));
         }
       }
