@@ -253,7 +253,10 @@ emissions_reg_kernel(const float* __restrict__ logits, const float* __restrict__
   const float zero_out = out_log ? logf(kTinyF) : 0.f;               // log(0 + tiny) = -87.33655
   const long long f_stride = (long long)gridDim.x * kEmisWarps;
   const long long f0 = (long long)blockIdx.x * kEmisWarps + w;
-  for (int i = lane; i < kRegWarpFloats; i += 32) base[i] = 0.f;     // lanes past n_bins read these (results unused)
+  for (int i = lane; i < kRegStages * kRegRow; i += 32) base[i] = 0.f;   // lanes past n_bins read these (results unused)
+  // the output row is the constant log(tiny) except at the peaks: filled ONCE; every frame writes its peaks, copies the
+  // row out and puts the constant back (3 scalar stores instead of a 1.5 KB refill)
+  for (int i = lane; i < kRegOut; i += 32) orow[i] = zero_out;
   __syncwarp();
   // frame -> ring stage st: voiced logits to x[0 .. n_bins), the unvoiced logit (model 0, column 0) to slot 0 of the
   // row (k = -8: outside every window).  A group is committed even when empty so that the wait count stays uniform.
@@ -380,16 +383,9 @@ emissions_reg_kernel(const float* __restrict__ logits, const float* __restrict__
     // output row at shift a: element k of the row sits at orow[a + k], so float4 j of orow is the 16-byte aligned
     // global float4 j of (out + f * S - a)
     const int total = a + S;
-    {
-      const float4 z4 = make_float4(zero_out, zero_out, zero_out, zero_out);
-      const int n4 = (total + 3) >> 2;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (lane + 32 * i < n4) reinterpret_cast<float4*>(orow)[lane + 32 * i] = z4;
-    }
-    __syncwarp();
+    const int k1 = a + (s1_unv ? n_bins : kb + i1);
     if (v0) orow[a + kb + i0] = p0v;
-    if (v1 || s1_unv) orow[a + (s1_unv ? n_bins : kb + i1)] = p1v;
+    if (v1 || s1_unv) orow[k1] = p1v;
     if (!unv_in_slot && lane == 0) orow[a + n_bins] = out_log ? logf(p_unv + kTinyF) : p_unv;
     __syncwarp();
     {
@@ -404,6 +400,10 @@ emissions_reg_kernel(const float* __restrict__ logits, const float* __restrict__
       const int tl = 4 * j1 + lane;
       if (lane < 4 && tl < total) oa[tl] = orow[tl];                 // tail
     }
+    __syncwarp();                                                    // the row has been copied: constant back in place
+    if (v0) orow[a + kb + i0] = zero_out;
+    if (v1 || s1_unv) orow[k1] = zero_out;
+    if (!unv_in_slot && lane == 0) orow[a + n_bins] = zero_out;
     __syncwarp();                                                    // orow and the stage are free again
     if (++st == kRegStages) st = 0;
     a = (a + a_step) & 3;
