@@ -20,6 +20,7 @@
 // One thread issues the 48 UTCHMMA of a step and commits them to an mbarrier; the step is a dependency chain
 // (wait V -> MMA -> epilogue -> exchange), so the tensor pipe is lightly used -- the point is the ~4x shorter chain than
 // the FFMA kernel's, not tensor throughput.
+#include <cstdio>
 #include <cstdlib>
 #include <cuda_bf16.h>
 
@@ -130,7 +131,8 @@ __global__ void __launch_bounds__(cThreads, 1)
 fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__ pi, const float* __restrict__ lik,
                   const int32_t* __restrict__ lengths, int B, int T_max, int S, TcPlan p, float* __restrict__ gamma,
                   float* __restrict__ cnorm, int dev) {
-  // dev: timing experiments only (results invalid): 1 = no HBM traffic, 2 = no exchange, 4 = no MMAs
+  // dev: timing experiments only: 1 = no HBM traffic, 2 = no exchange, 4 = no MMAs (results invalid); 8 = print the
+  // clock stamps of one step (results valid; needs -DVIT_FB_STAMPS)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int KP = p.KP, NCP = p.NCP;
   const uint32_t LBO = (cNN / 8) * 128;                 // bytes between groups of 8 K positions
@@ -138,18 +140,19 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
   const uint32_t buf_bytes = (uint32_t)KP * cNN * 2;    // hi + lo
   uint8_t* sV = smem_raw;                               // [2 buffers][KP/8][8 cores: 4 hi, 4 lo][8 k][8 n] bf16
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * buf_bytes);     // [0..1] V ready, [2] MMA done
-  __shared__ float s_c[2][cN];                          // 1 / normalisers of the step (forward: from D row 127)
+  __shared__ __align__(16) float s_c[2][cN];            // 1 / normalisers of the step (forward: from D row 127)
   __shared__ float s_craw[cN];
   __shared__ int s_len[cN];
   __shared__ uint32_t s_tmem_base;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & (cM - 1), half = tid >> 7, n0 = half * cH;     // my row (= TMEM lane) and my 16 clips
   const uint32_t C = cluster_nctarank();
   const uint32_t rank = cluster_ctarank();
   const int nc_mine = p.base + ((int)rank < p.rem ? 1 : 0);
   const int j = (int)rank * p.base + min((int)rank, p.rem) + row;      // my state
   const bool row_ok = row < nc_mine;
+  const float pi_j = (!BWD && row_ok) ? pi[j] : 0.f;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -233,11 +236,27 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
     int maxlen = 0;
     for (int n = 0; n < cN; ++n) maxlen = max(maxlen, s_len[n]);
     const int n_iter = BWD ? maxlen : maxlen + 1;         // forward: one extra MMA-only step yields the last normaliser
+    // lengths of my 16 clips in registers (0 for every clip of a row that holds no state): the step's loads and stores
+    // are then plain predicated instructions -- with the shared-memory reads inside, ptxas built a branch per clip and
+    // the epilogue was a serial chain of 16 x (LDS, branch, LDS, branch): 2800 of a step's 8100 clocks
+    int len_r[cH];
+#pragma unroll
+    for (int n = 0; n < cH; ++n) len_r[n] = row_ok ? s_len[n0 + n] : 0;
 
     bool first = true;
     for (int it = 0; it < n_iter; ++it, ++g) {
       const int t = BWD ? maxlen - 1 - it : it;
       const uint32_t cur = g & 1u, nxt = cur ^ 1u;
+#ifdef VIT_FB_STAMPS
+      // -DVIT_FB_STAMPS + VIT_DEV_FLAGS=8: clock stamps of one step of one CTA (thread 0), printed -- where the step's
+      // time goes (costs 36 registers, hence compile-time)
+      const bool stamp = (dev & 8) && it == 100 && blockIdx.x == 0 && tid == 0;
+      long long ck[10];
+      if (stamp) ck[0] = clock64();
+#define VIT_STAMP(i) do { if (stamp) ck[i] = clock64(); } while (0)
+#else
+#define VIT_STAMP(i) do { } while (0)
+#endif
       const bool tail = !BWD && it == maxlen;             // forward's extra step
       // this step's likelihoods (backwards also the stored alpha~): issued first, used after the MMAs
       float e[cH], al[cH];
@@ -248,14 +267,17 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
         const float* pn = p_t + (size_t)n0 * clip_stride;
 #pragma unroll
         for (int n = 0; n < cH; ++n, pn += clip_stride) {
-          const bool lv = row_ok && !tail && t < s_len[n0 + n] && !(dev & 1);
+          const bool lv = !tail && t < len_r[n] && !(dev & 1);
           e[n] = lv ? ld_global_nc_f32(pn) : 0.f;
           if (BWD) al[n] = lv ? ld_global_nc_f32(reinterpret_cast<const float*>(reinterpret_cast<const char*>(pn) + gamma_delta)) : 0.f;
         }
       }
       float d[cH];
+#pragma unroll
+      for (int n = 0; n < cH; ++n) d[n] = 0.f;
       if (!first) {
         if (C > 1 && !(dev & 2)) { mbar_wait_cta(smem_u32(&s_bar[cur]), ph[cur] & 1u); ++ph[cur]; }   // peers' rows of V have landed
+        VIT_STAMP(1);
         if (tid == 0 && !(dev & 4)) {
           // the K blocks of my own rows were issued at the end of the previous iteration (see below); now that the
           // peers' rows have landed, the other shards' K blocks follow and the batch is committed
@@ -270,7 +292,9 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
           const int n = tid & (cN - 1), tt = t + (tid >> 5);
           s_c[tid >> 5][n] = (tt < s_len[n]) ? 1.f / cnorm[(size_t)(seq0 + n) * T_max + tt] : 1.f;
         }
+        VIT_STAMP(2);
         if (!(dev & 4)) { mbar_wait_cta(smem_u32(&s_bar[2]), n_mma & 1u); ++n_mma; }
+        VIT_STAMP(3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {
           // D[:, 0:32] = M . V_hi, D[:, 32:64] = M . V_lo: my 16 clips of both halves
@@ -297,29 +321,39 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
         }
       }
       if (BWD && first && tid < cN) s_c[0][tid] = (t < s_len[tid]) ? 1.f / cnorm[(size_t)(seq0 + tid) * T_max + t] : 1.f;
+      VIT_STAMP(4);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();                                    // s_c visible; D fully read before the next MMA batch
+      VIT_STAMP(5);
       if (tail) { first = false; continue; }
 
       float v[cH];
       {
+        // 1 / c of my 16 clips: 4 (forward) or 8 (backward) independent LDS.128
+        float sc0[cH], sc1[cH];
+#pragma unroll
+        for (int q4 = 0; q4 < cH / 4; ++q4) {
+          const float4 a4 = reinterpret_cast<const float4*>(&s_c[0][n0])[q4];
+          sc0[4 * q4] = a4.x; sc0[4 * q4 + 1] = a4.y; sc0[4 * q4 + 2] = a4.z; sc0[4 * q4 + 3] = a4.w;
+          if (BWD) {
+            const float4 b4 = reinterpret_cast<const float4*>(&s_c[1][n0])[q4];
+            sc1[4 * q4] = b4.x; sc1[4 * q4 + 1] = b4.y; sc1[4 * q4 + 2] = b4.z; sc1[4 * q4 + 3] = b4.w;
+          }
+        }
         float* gn = reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<float*>(p_t)) + gamma_delta) + (size_t)n0 * clip_stride;
 #pragma unroll
         for (int n = 0; n < cH; ++n, gn += clip_stride) {
+          const bool lv = t < len_r[n];
           if (!BWD) {
             // alpha~_t = (M alpha~_{t-1} / c_{t-1}) * b_t ;  alpha~_0 = pi * b_0
-            float u;
-            if (first) u = row_ok ? pi[j] : 0.f;
-            else u = d[n] * s_c[0][n0 + n];
+            const float u = first ? pi_j : d[n] * sc0[n];
             v[n] = u * e[n];
-            if (row_ok && t < s_len[n0 + n] && !(dev & 1)) st_global_cs_f32(gn, v[n]);
+            if (lv && !(dev & 1)) st_global_cs_f32(gn, v[n]);
           } else {
             // beta_t = M w_{t+1} / c_{t+1} (1 at the clip's last frame); gamma_t = alpha~_t / c_t * beta_t; w_t = b_t beta_t
-            const int len = s_len[n0 + n];
-            const float be = (t == len - 1) ? 1.f : (first ? 0.f : d[n] * s_c[1][n0 + n]);
-            const bool lv = row_ok && t < len;
+            const float be = (t == len_r[n] - 1) ? 1.f : (first ? 0.f : d[n] * sc1[n]);
             v[n] = lv ? e[n] * be : 0.f;
-            if (lv && !(dev & 1)) st_global_cs_f32(gn, al[n] * s_c[0][n0 + n] * be);
+            if (lv && !(dev & 1)) st_global_cs_f32(gn, al[n] * sc0[n] * be);
           }
         }
       }
@@ -336,22 +370,35 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
         }
       }
       first = false;
+      VIT_STAMP(6);
       fence_proxy_async_smem();
       __syncthreads();
-      // my own rows of the next V are complete: start the next step's GEMM on their K blocks now (accumulator reset),
-      // under the exchange with the peers.  Every thread has read D (tcgen05.ld completed before the barrier above).
-      if (tid == 0 && !(dev & 4) && it + 1 < n_iter) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        issue_mma(nxt, (int)rank * NCP / 16, (int)rank * NCP / 16 + NCP / 16, 0);
-      }
-      if (C > 1 && !(dev & 2)) {
-        if (tid == 0) mbar_arrive_expect_tx(smem_u32(&s_bar[nxt]), tx_bytes);
-        if (tid < (int)(C - 1)) {
-          const uint32_t peer = (rank + 1 + tid) % C;
+      VIT_STAMP(7);
+      // my own rows of the next V are complete.  Warp 1 pushes them to the peers at once; warp 0 starts the next step's
+      // GEMM on their K blocks (accumulator reset) under the exchange.  (The push used to sit behind the 16 MMA issues
+      // in thread 0's program order, ~80 clocks each: the peers got their rows 1300 clocks late.)  Every thread has
+      // read D (tcgen05.ld completed before the barrier above).
+      if (C > 1 && !(dev & 2) && warp == 1) {
+        if (lane == 0) mbar_arrive_expect_tx(smem_u32(&s_bar[nxt]), tx_bytes);
+        if (lane < (int)(C - 1)) {
+          const uint32_t peer = (rank + 1 + lane) % C;
           const uint32_t src = smem_u32(sV + nxt * buf_bytes + (size_t)rank * slice_bytes);
           dsmem_bulk_copy(mapa(src, peer), src, slice_bytes, mapa(smem_u32(&s_bar[nxt]), peer));
         }
       }
+      if (tid == 0 && !(dev & 4) && it + 1 < n_iter) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_mma(nxt, (int)rank * NCP / 16, (int)rank * NCP / 16 + NCP / 16, 0);
+      }
+#ifdef VIT_FB_STAMPS
+      if (stamp) {
+        ck[8] = clock64();
+        printf("fb_tc step (%s): wait V %lld | issue MMA %lld | wait MMA %lld | tmem ld + norm %lld | sync1 %lld | epilogue %lld | "
+               "fence + sync2 %lld | own MMA + push %lld | total %lld clk\n", BWD ? "bwd" : "fwd", ck[1] - ck[0], ck[2] - ck[1],
+               ck[3] - ck[2], ck[4] - ck[3], ck[5] - ck[4], ck[6] - ck[5], ck[7] - ck[6], ck[8] - ck[7], ck[8] - ck[0]);
+      }
+#endif
+#undef VIT_STAMP
     }
     // backward: the rows pushed in the last step are never consumed -- wait for them so that every armed phase is
     // matched by exactly one wait (forward: the extra step consumed the last push)
