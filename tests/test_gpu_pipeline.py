@@ -98,6 +98,11 @@ def test_register_window_kernel_agrees_with_the_generic_kernel(pl, model, n_bins
         flat = torch.empty((a.numel() + 1,), dtype=torch.float32, device='cuda')
         c = pl.emissions_device(logits, n_bins, m, prior, 5, 0.3, out_log=out_log, out=flat[1:].view(a.shape))
         assert torch.equal(c, b)
+        # float4 rows at a per-frame alignment shift: nothing may land outside the table (canaries either side)
+        big = torch.full((a.numel() + 8,), float('nan'), dtype=torch.float32, device='cuda')
+        c2 = pl.emissions_device(logits, n_bins, m, prior, 5, 0.3, out_log=out_log, out=big[4:4 + a.numel()].view(a.shape))
+        assert torch.equal(c2, a)
+        assert bool(torch.isnan(big[:4]).all()) and bool(torch.isnan(big[-4:]).all())
 
 
 def test_voiced_bins_and_batched_pipeline(pl):
