@@ -111,6 +111,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* d) {
                : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// One leader lane of a converged warp (the same lane every time for the full mask).  Issuing tcgen05.mma under
+// `if (tid == 0)` makes ptxas wrap EVERY UTCHMMA in an ELECT / BRA.U.ANY loop over the "active threads" (~28 clocks per
+// MMA on top of the tensor pipe's floor); under warp-uniform control flow + elect.sync it is a straight instruction stream.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // 8 fp32 -> 8 bf16 hi (16 bytes) and 8 bf16 lo
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
@@ -278,7 +286,7 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
       if (!first) {
         if (C > 1 && !(dev & 2)) { mbar_wait_cta(smem_u32(&s_bar[cur]), ph[cur] & 1u); ++ph[cur]; }   // peers' rows of V have landed
         VIT_STAMP(1);
-        if (tid == 0 && !(dev & 4)) {
+        if (warp == 0 && !(dev & 4) && elect_one_sync()) {
           // the K blocks of my own rows were issued at the end of the previous iteration (see below); now that the
           // peers' rows have landed, the other shards' K blocks follow and the batch is committed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -386,7 +394,7 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
           dsmem_bulk_copy(mapa(src, peer), src, slice_bytes, mapa(smem_u32(&s_bar[nxt]), peer));
         }
       }
-      if (tid == 0 && !(dev & 4) && it + 1 < n_iter) {
+      if (warp == 0 && !(dev & 4) && it + 1 < n_iter && elect_one_sync()) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         issue_mma(nxt, (int)rank * NCP / 16, (int)rank * NCP / 16 + NCP / 16, 0);
       }
