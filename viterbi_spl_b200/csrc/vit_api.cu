@@ -89,8 +89,8 @@ size_t fb_tc_workspace_bytes(int B, int T_max, int S);
 int fb_tc_run(const float* A, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S,
               void* workspace, size_t workspace_bytes, float* gamma, float* loglik, cudaStream_t stream);
 // Which of the two forward-backward kernels runs: the tcgen05 tensor-core kernel wherever the shape fits (S <= 381: the
-// bf16 hi/lo image of a 127-row shard plus the accumulators must fit the 512 TMEM columns) -- measured 34.4 ms vs the
-// FFMA kernel's 46.2 ms at 1024 x 3000 x 361 and 35.0 vs 61.6 ms at 4096 x 1000 x 361 -- else the FFMA kernel (S = 722).
+// bf16 hi/lo image of a 127-row shard plus the accumulators must fit the 512 TMEM columns) -- measured 19.2 ms vs the
+// FFMA kernel's 46.2 ms at 1024 x 3000 x 361 -- else the FFMA kernel (S = 722).
 // VIT_FB_IMPL=tc|simt forces one of them where the shape allows (tests run both).
 static bool fb_use_tc(int B, int S) {
   (void)B;
