@@ -157,6 +157,82 @@ def imm_viterbi_class():
     return ref_toplevel('imm/tf_imm.py', 'Viterbi', extra={'gen_transition_matrix_fn': gen, 'tf': _TF})
 
 
+class _NPTensor(np.ndarray):
+    """ndarray that answers the two tf.Tensor methods the reference's peak finder calls on its intermediate values."""
+
+    def numpy(self):
+        return np.asarray(self)
+
+    def set_shape(self, shape):
+        assert len(shape) == self.ndim and all(a is None or a == b for a, b in zip(shape, self.shape))
+
+
+class _FakeSignal:
+    @staticmethod
+    def frame(x, frame_length, frame_step, axis=-1):
+        assert frame_step == 1 and axis == -1
+        return np.lib.stride_tricks.sliding_window_view(np.asarray(x), frame_length, axis=-1).view(_NPTensor)
+
+
+class FakeTF:
+    """NumPy stand-ins for the handful of TensorFlow calls inside ``Viterbi.find_peaks_all_at_once_tf_fn``
+    (dcnet/softmax_viterbi.py:2294-2314: convert_to_tensor, pad(reflect), signal.frame, argmax) so that the reference's
+    own ``observation_probs_fn`` / ``__call__`` of the dcnet and msnet ``class Viterbi`` can be EXECUTED here without
+    TensorFlow.  ``tf.argmax`` documents no tie order; NumPy's first maximum is the pinned behaviour."""
+    int32 = np.int32
+    float32 = np.float32
+    Tensor = _NPTensor
+    Variable = _FakeTFVar
+    signal = _FakeSignal
+
+    @staticmethod
+    def function(*a, **kw):
+        return (lambda f: f) if not (a and callable(a[0])) else a[0]
+
+    @staticmethod
+    def TensorSpec(*a, **kw):
+        return None
+
+    @staticmethod
+    def convert_to_tensor(x, dtype=None):
+        return np.asarray(x, dtype).view(_NPTensor)
+
+    @staticmethod
+    def pad(x, paddings, mode='constant'):
+        return np.pad(np.asarray(x), paddings, mode=mode.lower()).view(_NPTensor)
+
+    @staticmethod
+    def argmax(x, axis=-1, output_type=np.int64):
+        return np.argmax(np.asarray(x), axis=axis).astype(output_type).view(_NPTensor)
+
+
+# (file, class) of every ``class Viterbi`` / ``class SoftMaxViterbi`` copy the drop-in namespaces mirror
+CLASS_COPIES = {
+    ('dcnet', 'Viterbi'): 'dcnet/softmax_viterbi.py', ('dcnet', 'SoftMaxViterbi'): 'dcnet/softmax_viterbi.py',
+    ('msnet', 'Viterbi'): 'msnet/viterbi_softmax.py', ('msnet', 'SoftMaxViterbi'): 'msnet/viterbi_softmax.py',
+    ('ftanet', 'Viterbi'): 'ftanet/viterbi_performance.py', ('ftanet', 'SoftMaxViterbi'): 'ftanet/viterbi_performance.py',
+    ('jdc', 'Viterbi'): 'jdc/viterbi_softmax.py', ('jdc', 'SoftMaxViterbi'): 'jdc/viterbi_softmax.py',
+    ('tonet', 'Viterbi'): 'tonet/softmax_priors.py', ('tonet', 'SoftMaxViterbi'): 'tonet/softmax_priors.py',
+    ('tonet', 'ViterbiA'): 'tonet/main_shaun.py', ('tonet', 'SoftMaxViterbiAlwaysScaled'): 'tonet/ablation.py',
+    ('tonet', 'SoftMaxViterbiWide'): 'tonet/for_paper.py',
+    ('imm', 'Viterbi'): 'imm/main_imm.py',
+}
+
+
+def reference_class(namespace, name):
+    """The reference's own class object for one entry of CLASS_COPIES (AST-exec'd, TensorFlow stubbed by FakeTF)."""
+    relpath = CLASS_COPIES[(namespace, name)]
+    cls_name = {'ViterbiA': 'Viterbi', 'SoftMaxViterbiAlwaysScaled': 'SoftMaxViterbi',
+                'SoftMaxViterbiWide': 'SoftMaxViterbi'}.get(name, name)
+    return ref_toplevel(relpath, cls_name, extra={'load_np_array_from_file_fn': dat_loader(), 'tf': FakeTF})
+
+
+def construct_in(directory, cls, *args, **kw):
+    """Run a reference constructor with `directory` as the working directory (they read their .dat files from cwd)."""
+    with _Chdir(directory):
+        return cls(*args, **kw)
+
+
 def imm_gen_transition_matrix():
     return ref_toplevel('imm/transition_matrix.py', 'gen_transition_matrix_fn')
 

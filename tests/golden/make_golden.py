@@ -150,5 +150,53 @@ def main():
          log_pi=np.array(tv.log_ini_probs))
 
 
+def class_calls():
+    """7. The class-level call the pipelines make (``voiced, bins = viterbi_ins(logits)``, dcnet/softmax_viterbi.py:3039)
+    for every copy of ``class Viterbi`` / ``class SoftMaxViterbi`` (tests/class_cases.py lists them), by constructing the
+    reference's own class in a directory holding the parameter files and calling its ``observation_probs_fn`` and
+    ``__call__``; plus imm/tf_imm.py's HF0 decoder.  -> class_calls.npz"""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import class_cases as cc
+    tiny = np.finfo(np.float32).tiny
+    out = {}
+    dirs = {}
+    keep = []
+    for state_set in ('msnet_shipped', 'tonet', 'jdc', 'imm_hmm'):
+        A, pi = cc.parameters(state_set, rl.REF_ROOT)
+        d = tempfile.TemporaryDirectory()
+        keep.append(d)
+        cc.write_dat(d.name, A, pi)
+        dirs[state_set] = d.name
+        out[f'A_{state_set}'] = A
+        out[f'pi_{state_set}'] = pi
+    for case in cc.CASES:
+        ns, name, args, state_set, _ = case
+        tag = cc.case_tag(case)
+        ref = rl.construct_in(dirs[state_set], rl.reference_class(ns, name), *cc.ctor_args(args, rl.FakeTF.Variable))
+        logits = cc.logits_for(case, seed=sum(map(ord, tag)))
+        probs = ref.observation_probs_fn(logits.copy())
+        voiced, bins = ref(logits.copy())
+        out[f'{tag}_logits'] = logits
+        out[f'{tag}_probs'] = probs
+        out[f'{tag}_log_probs'] = np.log(probs + tiny)                  # what the decoder sees (machine-independent replay)
+        out[f'{tag}_voiced'] = voiced
+        out[f'{tag}_bins'] = bins
+        out[f'{tag}_exp_probe'] = np.exp(logits[:4].astype(np.float32))  # detects a different libm on replay
+        print(f'  {tag:44s} T={len(bins):4d} voiced {voiced.mean():.2f}')
+    imm = rl.imm_viterbi_class()(20, 721)
+    HF0 = cc.hf0_case(5)
+    log_HF0 = imm.process_HF0_fn(HF0)
+    out['imm_HF0Viterbi_HF0'] = HF0
+    out['imm_HF0Viterbi_log_HF0'] = log_HF0
+    out['imm_HF0Viterbi_states'] = imm(HF0)
+    out['imm_HF0Viterbi_logA_T_sha'] = np.array(sha(imm.log_transition_matrix_T))
+    save('class_calls.npz', **out)
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'class_calls':
+        class_calls()
+    else:
+        main()
+        class_calls()

@@ -113,6 +113,17 @@ def test_reference_entry_points(Decoder):
     got = api.viterbi_librosa_fn(log_transition_matrix_T=g['logA_T'], log_prob_init=g['log_pi'],
                                  log_probs_st=np.require(g['log_probs_ts'].T, requirements=['C']))
     assert np.array_equal(got, g['states'])
+    # float64 initial log-probabilities: the reference adds T1[0] in float64 and rounds once (imm/tf_viterbi.py:94)
+    pi64 = g['log_pi'].astype(np.float64) + 1e-9
+    E_st = np.require(g['log_probs_ts'].T, requirements=['C'])
+    got = api.viterbi_librosa_fn(log_transition_matrix_T=g['logA_T'], log_prob_init=pi64, log_probs_st=E_st)
+    assert np.array_equal(got, np_oracle.viterbi_log_np(g['logA_T'], np.zeros_like(g['log_pi']),
+                                                        np.concatenate([(pi64 + g['log_probs_ts'][0]).astype(np.float32)[None],
+                                                                        g['log_probs_ts'][1:]]))[0])
+    with pytest.raises(AssertionError):
+        api.viterbi_librosa_c_fn(transition_matrix=g['A'].astype(np.float64), prob_init=g['pi'], probs_st=probs_f)
+    assert np.array_equal(api.viterbi_librosa_f64_fn(transition_matrix=g['A'], prob_init=g['pi'], probs_st=probs_f),
+                          g['states_f64'] if same_libm else want)         # a7: float64-table variant, same paths here
     # eager-TF twin of the log-domain function (imm/tf_viterbi.py:8): same math, int32 result, any emission layout
     got = api.tf_viterbi_librosa_fn(tf_log_transition_matrix_T=g['logA_T'], tf_log_prob_init=g['log_pi'],
                                     tf_or_np_log_probs_st=g['log_probs_ts'].T)
@@ -120,7 +131,7 @@ def test_reference_entry_points(Decoder):
 
     # Family B (tonet): F-ordered prob-domain [S, T], logged in place
     b = load('tonet_family_b.npz')
-    vb = api.ViterbiB(b['A'], b['pi'])
+    vb = api.ViterbiB(0.5, transition_matrix=b['A'], ini_probs=b['pi'])     # tonet/softmax_priors.py:1693 Viterbi(voicing_threshold)
     assert np.array_equal(vb.log_transition_matrix_T, b['logA_T']) or not same_libm
     probs = np.asfortranarray(b['probs_st'])
     want_b = b['states'] if np.array_equal(np.log(b['probs_st'] + tiny), b['log_probs_st']) else \
@@ -133,16 +144,16 @@ def test_reference_entry_points(Decoder):
     voiced, bins = api.voiced_and_bins(got, 360)
     if want_b is b['states']:
         assert np.array_equal(voiced, b['voiced']) and np.array_equal(bins, b['bins'])
+        v2, b2 = vb(b['logits'].copy())                                    # the class-level call: logits -> (voiced, bins)
+        assert np.array_equal(v2, b['voiced']) and np.array_equal(b2, b['bins'])
 
     # Family C (msnet shipped parameters): C-ordered prob-domain [T, S]
     m = load('msnet_softmax_viterbi.npz')
     ml = load('msnet_logdomain.npz')
-    A_lin = np.exp(ml['logA_T'].T.astype(np.float64)).astype(np.float32)
-    A_lin[ml['logA_T'].T < -80] = 0
-    A_lin = (A_lin / A_lin.sum(1, keepdims=True)).astype(np.float32)
-    sv = api.SoftMaxViterbi(A_lin, ml['ini_probs'], scaled=True)
-    sv.log_transition_matrix_T = ml['logA_T']                                # use the exact shipped log matrix
-    sv._decoder = Decoder(ml['logA_T'], ml['log_pi'])
+    A_lin = np.load(os.path.join(GOLD, 'class_calls.npz'))['A_msnet_shipped']   # the shipped msnet/*.dat matrix
+    sv = api.msnet.SoftMaxViterbi(True, transition_matrix=A_lin, ini_probs=ml['ini_probs'])
+    assert np.array_equal(sv.log_transition_matrix_T, ml['logA_T']) or not same_libm
+    sv.__dict__['_decoder_obj'] = Decoder(ml['logA_T'], ml['log_pi'])       # decode with the exact shipped log matrix
     for scaled in (0, 1):
         probs = m[f'prob_ts_{scaled}'].copy()
         if not np.array_equal(np.log(probs + tiny), m[f'log_prob_ts_{scaled}']):

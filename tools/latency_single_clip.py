@@ -21,7 +21,9 @@ for name, S in (('dcnet', 321), ('tonet', 361), ('jdc', 722)):
         st = api.viterbi_librosa_fn(log_transition_matrix_T=logA_T, log_prob_init=log_pi, log_probs_st=E_st)
         ts.append(time.perf_counter() - t0)
     # Family C object (dcnet/softmax_viterbi.py:2636): prob-domain [T, S], logged in place on the host
-    sv = api.SoftMaxViterbi(A, pi) if np.argmax(pi) == S - 1 else None
+    ns = {321: api.msnet, 361: api.tonet, 722: api.jdc}.get(S)
+    sv = ns.SoftMaxViterbi(False, transition_matrix=np.asarray(A, np.float32), ini_probs=np.asarray(pi, np.float32)) \
+        if (ns is not None and np.argmax(pi) == S - 1) else None
     tc = []
     if sv is not None:
         P = np.exp(E)

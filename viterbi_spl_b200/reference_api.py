@@ -16,9 +16,12 @@ numba      dcnet/tf_viterbi_decoding.py:119 ``viterbi_numba_fn``,        ``viter
            dcnet/aot_viterbi_core.py:8 ``viterbi_numba.core``
 TF         dcnet/tf_viterbi_decoding.py:23 ``viterbi_tf_fn``,            ``viterbi_tf_fn``, ``tf_viterbi_librosa_fn``
            imm/tf_viterbi.py:8 ``tf_viterbi_librosa_fn``                 (NumPy in, int32 out)
-B          tonet/softmax_priors.py:1841 ``Viterbi.viterbi_librosa_fn``   ``ViterbiB.viterbi_librosa_fn``
-C          dcnet/softmax_viterbi.py:2636 ``SoftMaxViterbi...``           ``SoftMaxViterbi.viterbi_librosa_fn``
-D (class)  imm/tf_imm.py:90 ``Viterbi.viterbi_librosa_fn``               ``ImmViterbi.viterbi_librosa_fn``
+f64 table  dcnet/tf_viterbi_decoding.py:209 ``viterbi_librosa_fn``        ``viterbi_librosa_f64_fn`` (same paths, fp32)
+classes    ``Viterbi`` / ``SoftMaxViterbi`` of every directory           ``dcnet. msnet. ftanet. jdc. tonet. imm.``
+           (ctor, observation_probs_fn, __call__ -> voiced, bins)        namespaces (reference_classes.py)
+B          tonet/softmax_priors.py:1841 ``Viterbi.viterbi_librosa_fn``   ``tonet.Viterbi.viterbi_librosa_fn``
+C          dcnet/softmax_viterbi.py:2636 ``SoftMaxViterbi...``           ``dcnet.SoftMaxViterbi.viterbi_librosa_fn``
+D (class)  imm/tf_imm.py:90 ``Viterbi.viterbi_librosa_fn``               ``imm.HF0Viterbi.viterbi_librosa_fn``
 =========  ===========================================================  =======================================
 """
 import hashlib
@@ -27,7 +30,6 @@ from collections import OrderedDict
 
 import numpy as np
 
-from . import hmm_params
 from .decoder import ViterbiDecoder
 
 TINY = np.finfo(np.float32).tiny
@@ -60,10 +62,30 @@ def _decoder_for(log_transition_matrix_T, log_prob_init):
     return dec
 
 
+def _float32_parameters(B, prob_init, first_row):
+    """The recursion the GPU runs is float32 throughout, like the reference's when its parameters are float32 (what its
+    .dat files hold).  With a float64 ``prob_init`` the reference's ``T1[0] = prob_init + probs[0]`` (imm/tf_viterbi.py:94)
+    adds in float64 and rounds ONCE into the float32 table: reproduced here by doing that one row on the host and handing
+    the decoder a zero initial vector (0 + x is exact).  A float64 transition matrix would make every ``T1[t-1] + B`` of
+    the reference a float64 add rounded to float32 -- not what this decoder computes, so it is refused rather than
+    silently rounded twice."""
+    assert B.dtype == np.float32, ('transition parameters must be float32 (a float64 matrix makes the reference add in '
+                                   'float64 at every step; cast it to float32 first)')
+    prob_init = np.asarray(prob_init)
+    if prob_init.dtype == np.float32:
+        return prob_init, None
+    row0 = (prob_init + first_row).astype(np.float32)                # float64 add, one rounding
+    return np.zeros(len(prob_init), np.float32), row0
+
+
 def _decode_ts(log_transition_matrix_T, log_prob_init, log_probs_ts):
     """[T, S] log emissions -> int64[T] via the GPU decoder."""
     E = np.require(log_probs_ts, np.float32, ['C'])
     assert not np.isnan(E.min()), 'emissions contain NaN'            # (min propagates NaN: one pass, no temporary)
+    log_prob_init, row0 = _float32_parameters(log_transition_matrix_T, log_prob_init, E[0] if len(E) else None)
+    if row0 is not None and len(E):
+        E = E.copy()
+        E[0] = row0
     paths, _ = _decoder_for(log_transition_matrix_T, log_prob_init).decode_host(E[None])
     return paths[0]
 
@@ -72,7 +94,7 @@ def _decode_st(log_transition_matrix_T, log_prob_init, log_probs_st):
     """[S, T] log emissions, C-contiguous -> int64[T].  The transpose the reference does on the host
     (imm/tf_viterbi.py:89, a strided copy of the whole table) happens on the GPU after the upload instead."""
     E = log_probs_st
-    if not E.flags['C_CONTIGUOUS']:
+    if not E.flags['C_CONTIGUOUS'] or np.asarray(log_prob_init).dtype != np.float32:
         return _decode_ts(log_transition_matrix_T, log_prob_init, np.require(E.T, np.float32, ['C']))
     assert not np.isnan(E.min()), 'emissions contain NaN'
     paths, _ = _decoder_for(log_transition_matrix_T, log_prob_init).decode_host_st(E)
@@ -133,6 +155,15 @@ def viterbi_librosa_c_fn(*, transition_matrix, prob_init, probs_st):
     return _family_a(transition_matrix, prob_init, probs_st)
 
 
+def viterbi_librosa_f64_fn(*, transition_matrix, prob_init, probs_st):
+    """dcnet/tf_viterbi_decoding.py:209-263 -- the module's plain ``viterbi_librosa_fn``, whose ``T1`` table is float64
+    (``np.empty([T, S])``, :242), so ITS recursion adds in double.  Same signature and checks; the decode here is the
+    float32 one of ``viterbi_librosa_c_fn`` (the parity target): the two agree wherever no
+    two candidate paths are within float32 rounding of each other (equal on the golden inputs,
+    tests/golden/family_a.npz ``states_f64``), but a near-tie can resolve differently than in the float64 table."""
+    return _family_a(transition_matrix, prob_init, probs_st)
+
+
 def viterbi_numba_fn(*, transition_matrix, prob_init, probs_st):
     """dcnet/tf_viterbi_decoding.py:119-153: validates, transposes, calls the compiled core."""
     B = transition_matrix
@@ -160,12 +191,12 @@ class viterbi_numba:  # noqa: N801  (module name in the reference)
         export it overwrites all three inputs with their logs (dcnet/aot_viterbi_core.py:23-25)."""
         assert B.dtype == np.float32 and prob_init.dtype == np.float32 and probs.dtype == np.float32
         assert B.flags['C_CONTIGUOUS'] and probs.flags['C_CONTIGUOUS']
-        tinyp = np.float32(1.1754944e-38)                            # :18
-        S = B.shape[0]
+        tinyp = 1.1754944e-38                                        # :18 -- a float64 literal: numba promotes B + tinyp
+        S = B.shape[0]                                               # to float64, logs in float64 and rounds once to f4
         assert prob_init.shape[0] == S                               # :22
-        B[:] = np.log(B + tinyp)
-        prob_init[:] = np.log(prob_init + tinyp)
-        probs[:] = np.log(probs + tinyp)
+        B[:] = np.log(B.astype(np.float64) + tinyp)
+        prob_init[:] = np.log(prob_init.astype(np.float64) + tinyp)
+        probs[:] = np.log(probs.astype(np.float64) + tinyp)
         return _decode_ts(B, prob_init, probs)
 
 
@@ -183,123 +214,20 @@ def viterbi_tf_fn(transition_matrix, prob_init, probs_st):
     return _decode_ts(B, pi, probs).astype(np.int32)
 
 
-# ---- decoder objects (Families A-D) -----------------------------------------------------------------------------------
+# ---- decoder objects (Families A-D): the classes the pipelines construct and call -----------------------------------
+#
+# One namespace per experiment directory of the reference, each holding that directory's ``Viterbi`` / ``SoftMaxViterbi``
+# with the reference's constructor signature, ``find_peaks_all_at_once_np_fn``, ``observation_probs_fn``,
+# ``viterbi_librosa_fn`` and ``__call__(logits) -> (voiced, bins)`` (viterbi_spl_b200/reference_classes.py).  A pipeline
+# switches with one import line, e.g. in dcnet/softmax_viterbi.py
+#     from viterbi_spl_b200.reference_api import dcnet; Viterbi, SoftMaxViterbi = dcnet.Viterbi, dcnet.SoftMaxViterbi
+# instead of the class definitions at :2273 and :2488.
+from .reference_classes import HF0Viterbi, dcnet, ftanet, imm, jdc, msnet, tonet  # noqa: E402,F401
 
-class Viterbi:
-    """Family A object (dcnet/softmax_viterbi.py:2273-2485): linear parameters, static decode."""
-
-    def __init__(self, transition_matrix, ini_probs, num_freq_bins=None):
-        t = np.sum(transition_matrix, axis=1)
-        assert np.all(np.isclose(t, 1))                               # :2413-2414
-        assert np.all(ini_probs > 0)                                  # :2381
-        self.transition_matrix = transition_matrix
-        self.ini_probs = ini_probs
-        self.num_freq_bins = len(ini_probs) - 1 if num_freq_bins is None else num_freq_bins
-
-    @staticmethod
-    def viterbi_librosa_fn(*, transition_matrix, prob_init, probs_st):
-        """dcnet/softmax_viterbi.py:2433-2485 (11 copies across the reference)."""
-        return _family_a(transition_matrix, prob_init, probs_st)
-
-    def decode_probs(self, observation_probs):
-        """The tail of ``__call__`` (:2421-2431): decode, then voiced = bins < n_bins; bins = min(bins, n_bins-1)."""
-        bins = Viterbi.viterbi_librosa_fn(transition_matrix=self.transition_matrix, prob_init=self.ini_probs,
-                                          probs_st=observation_probs)
-        return voiced_and_bins(bins, self.num_freq_bins)
-
-
-class _LogParamDecoder:
-    """Shared ctor of Families B/C: log(x + tiny), transpose, float32 C-contiguous, read-only
-    (tonet/softmax_priors.py:1788-1823; dcnet/softmax_viterbi.py:2581-2618)."""
-
-    def __init__(self, transition_matrix, ini_probs, num_freq_bins=None):
-        U = len(ini_probs) - 1 if num_freq_bins is None else num_freq_bins
-        self.num_freq_bins = U
-        assert ini_probs.shape == (U + 1,)
-        assert np.isclose(np.sum(ini_probs), 1)
-        assert transition_matrix.shape == (U + 1, U + 1)
-        assert np.all(np.isclose(np.sum(transition_matrix, axis=1), 1))
-        self.ini_probs = ini_probs
-        self.log_transition_matrix_T, self.log_ini_probs = hmm_params.log_params(transition_matrix, ini_probs)
-        self.log_transition_matrix_T.flags['WRITEABLE'] = False
-        self.log_ini_probs.flags['WRITEABLE'] = False
-        self._decoder = ViterbiDecoder(self.log_transition_matrix_T, self.log_ini_probs)
-
-    @classmethod
-    def from_dat(cls, directory='.', **kw):
-        """Load ``viterbi_transition_matrix.dat`` / ``viterbi_init_probs.dat`` like the reference ctors do."""
-        import os
-        name, A = hmm_params.load_dat(os.path.join(directory, 'viterbi_transition_matrix.dat'))
-        assert name == 'viterbi_transition_matrix'
-        name, pi = hmm_params.load_dat(os.path.join(directory, 'viterbi_init_probs.dat'))
-        assert name == 'viterbi_init_probs'
-        return cls(A, pi, **kw)
-
-    def _decode(self, log_probs_ts):
-        paths, _ = self._decoder.decode_host(np.require(log_probs_ts, np.float32, ['C'])[None])
-        return paths[0]
-
-    def decode_probs(self, probs):
-        return voiced_and_bins(self.viterbi_librosa_fn(probs), self.num_freq_bins)
-
-
-class ViterbiB(_LogParamDecoder):
-    """Family B (tonet/softmax_priors.py:1691-1878 and the imm-HMM copies)."""
-
-    def viterbi_librosa_fn(self, probs_st):
-        """``probs_st [S, T]`` float32 F-contiguous, prob-domain; LOGGED IN PLACE (:1854-1857)."""
-        S = self.num_freq_bins + 1
-        assert probs_st.shape[0] == S
-        assert probs_st.dtype == np.float32
-        assert probs_st.flags['F_CONTIGUOUS'] == True  # noqa: E712
-        np.add(probs_st, TINY, out=probs_st)
-        np.log(probs_st, out=probs_st)
-        probs = np.require(probs_st.T, np.float32, ['C'])
-        return self._decode(probs)
-
-
-class SoftMaxViterbi(_LogParamDecoder):
-    """Family C (dcnet/softmax_viterbi.py:2488-2674 and 6 more copies): the north star's "posteriors [T, N]" layout."""
-
-    def __init__(self, transition_matrix, ini_probs, scaled=False, num_freq_bins=None):
-        super().__init__(transition_matrix, ini_probs, num_freq_bins)
-        assert np.argmax(ini_probs) == self.num_freq_bins              # unvoiced (last) is the most likely start, :2589
-        assert np.all(ini_probs > 0)
-        self.scaled = scaled
-
-    def viterbi_librosa_fn(self, probs_ts):
-        """``probs_ts [T, S]`` float32 C-contiguous, prob-domain (may exceed 1 when scaled); LOGGED IN PLACE (:2650-2653)."""
-        S = self.num_freq_bins + 1
-        assert probs_ts.ndim == 2
-        assert probs_ts.shape[1] == S
-        assert probs_ts.dtype == np.float32
-        assert probs_ts.flags['C_CONTIGUOUS']
-        np.add(probs_ts, TINY, out=probs_ts)
-        np.log(probs_ts, out=probs_ts)
-        return self._decode(probs_ts)
-
-
-class ImmViterbi:
-    """Family D object (imm/tf_imm.py:48-135): fully dense transition matrix from the IMM recipe, uniform pi."""
-
-    def __init__(self, bins_per_semitone, n_bins):
-        self.b = bins_per_semitone
-        self.n_bins = n_bins
-        A = hmm_params.dense_imm_transition_matrix(bins_per_semitone, n_bins)      # :54
-        assert np.all(A > 0)
-        init = np.full([n_bins + 1], 1. / (n_bins + 1))                            # :62-64
-        self.log_transition_matrix_T, self.log_prob_init = hmm_params.log_params(A, init, add_tiny=False)
-        self._decoder = ViterbiDecoder(self.log_transition_matrix_T, self.log_prob_init)
-
-    def viterbi_librosa_fn(self, log_HF0):
-        """``log_HF0 [S, T]`` float32 log-domain (:90-127)."""
-        S = self.n_bins + 1
-        assert isinstance(log_HF0, np.ndarray)
-        assert log_HF0.dtype == np.float32
-        assert log_HF0.shape[0] == S
-        probs = np.require(np.transpose(log_HF0), np.float32, ['C'])
-        paths, _ = self._decoder.decode_host(probs[None])
-        return paths[0]
+Viterbi = dcnet.Viterbi                   # dcnet/softmax_viterbi.py:2273  Viterbi()                 (Family A, static decode)
+SoftMaxViterbi = dcnet.SoftMaxViterbi     # dcnet/softmax_viterbi.py:2488  SoftMaxViterbi(voicing_threspold_prob, scaled)  (C)
+ViterbiB = tonet.Viterbi                  # tonet/softmax_priors.py:1691   Viterbi(voicing_threshold)                    (B)
+ImmViterbi = HF0Viterbi                   # imm/tf_imm.py:48               Viterbi(bins_per_semitone, n_bins)            (D)
 
 
 def voiced_and_bins(states, n_bins):
