@@ -11,6 +11,13 @@ One "step" = one pass of the decoder (forward recursion + backtrace) over one ba
            CUDA events recorded by the library around that kernel; `roofline_hbm` gives the same launch in GB/s.
 `cpu_baseline`: the NumPy restatement of the reference decode (oracle/np_oracle.py, the reference's own CPU path is
            NumPy) on a bounded sample of the same workload over all host cores.
+Extra keys of the same line (the other BASELINE.json configurations at their named sizes, each with an oracle check):
+`forward_backward` : config 4 -- scaled forward-backward posteriors, 1024 x 3000 x 361 (tcgen05): ms, frames/s, HBM
+           fraction, max |gamma - float64 oracle| on 3 clips.
+`cfg3_stream`: config 3's kernel -- S = 722 with logA^T streamed from L2 through the bulk-copy (TMA) ring: one full pass
+           of 2072 clips x 500 frames, fraction of the FP32 max-plus peak, 2 clips against the oracle.
+`strong` : config 5's sweep -- 65,536 clips x 3000 x 361 sharded over the N ranks (65,536 / N clips per GPU, decoded in
+           HBM-sized waves generated on the device): total frames/s, i.e. STRONG scaling when run at N = 1, 2, 4, 8.
 Under torchrun every rank decodes its own batch of the same shape (clips are independent: weak scaling, no collective
 on the data path); rank 0 prints ONE JSON line.
 """
@@ -46,7 +53,16 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=12.0, help='target wall time of the cpu_baseline sample')
+    ap.add_argument('--no-extras', action='store_true', help='skip the forward_backward / cfg3_stream / strong legs')
+    ap.add_argument('--strong-clips', type=int, default=65536, help='total clips of the strong-scaling leg (config 5)')
     return ap.parse_args()
+
+
+def shared_config(a):
+    """The `config` object -- identical in both arms (`--impl ours` and `--impl reference`): it names the workload; what is
+    specific to an arm (kernel, parallelism; the CPU arm's sampling) lives in `details` / `sample`."""
+    return {'workload': workload_name(a), 'clips_per_gpu': a.clips, 'frames': a.frames, 'states': a.states,
+            'l2': f'no flush needed: one step reads {a.clips * a.frames * a.states * 4 / 1e9:.1f} GB of emissions, far more than the 126 MB L2'}
 
 
 def workload_name(a):
@@ -130,13 +146,13 @@ def run_reference(a):
     total = sum(times)
     fps = frames * len(times) / total
     sample = (f'{cores * clips_per_core} clips x {a.frames} frames x {a.states} states per step '
-              f'({clips_per_core} per core x {cores} processes)')
+              f'({clips_per_core} per core x {cores} processes, all host cores whatever --gpus is); NumPy restatement of '
+              f'imm/tf_viterbi.py:75-109 (the reference is pure Python/NumPy; TensorFlow is not installed)')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
         'warmup': a.warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(a), 'clips': a.clips, 'frames': a.frames, 'states': a.states,
-                   'sample_per_step': sample},
+        'config': shared_config(a), 'sample': sample,
         'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -224,6 +240,192 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+
+# ---- the other BASELINE.json configurations (extra keys of the line) -----------------------------------------------
+
+def leg_forward_backward(dev, world, barrier, all_max, peaks, steps=3):
+    """Config 4: scaled forward-backward posteriors, 1024 clips x 3000 frames x 361 states per GPU (tcgen05 kernel)."""
+    import torch
+    from viterbi_spl_b200 import ForwardBackward, _lib, hmm_params
+    B, T, S = 1024, 3000, 361
+    A, pi = hmm_params.synthetic_hmm('tonet')
+    A, pi = A.astype(np.float32), pi.astype(np.float32)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)
+    lik = torch.softmax(2.0 * torch.randn((B, T, S), device=dev, generator=g), dim=-1)    # dense softmax likelihoods
+    fb = ForwardBackward(A, pi, device=dev)
+    gamma = torch.empty_like(lik)
+    ll = torch.empty(B, device=dev)
+    fb.run_device(lik, None, gamma, ll)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    n0 = _lib.launch_count()
+    e0.record()
+    for _ in range(steps):
+        fb.run_device(lik, None, gamma, ll)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms = all_max(e0.elapsed_time(e1) / steps)
+    out = {'workload': f'scaled forward-backward posteriors: {B} clips x {T} frames x {S} states per GPU', 'dtype': 'f32 '
+           '(products as 2 x bf16 terms on tcgen05, fp32 accumulate)', 'ms_per_step': ms, 'steps': steps,
+           'value': world * B * T / (ms * 1e-3), 'unit': UNIT, 'gpu_launches': int(launches)}
+    hbm = float(peaks.get('hbm_gbs', 6650.0))
+    bytes_ = 20.0 * B * T * S           # SURVEY 8(d): b read twice, alpha~ written and read, gamma written
+    out['roofline_hbm'] = {'bound': 'hbm', 'achieved': bytes_ / (ms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                           'frac': bytes_ / (ms * 1e-3) / 1e9 / hbm, 'algorithmic_bytes': bytes_}
+    flops = 2.0 * 2.0 * B * (T - 1) * S * S       # fwd + bwd, 2 flop per cell (useful fp32-equivalent work)
+    out['useful_tflops'] = flops / (ms * 1e-3) / 1e12
+    try:
+        from oracle import fb_oracle
+        sub = [0, B // 2, B - 1]
+        wg, wl = fb_oracle.forward_backward_batch_np(A, pi, lik[sub].cpu().numpy())
+        out['parity_vs_float64_oracle'] = {'max_abs_gamma_err': float(np.abs(gamma[sub].cpu().numpy() - wg).max()),
+                                           'max_rel_loglik_err': float(np.abs((ll[sub].cpu().numpy() - wl) / wl).max()),
+                                           'clips_checked': len(sub), 'tolerance': 'gamma 1e-4 abs, log L 1e-5 rel'}
+    except Exception as ex:
+        out['parity_vs_float64_oracle'] = f'oracle unavailable: {ex}'
+    return out
+
+
+def leg_cfg3_stream(dev, world, barrier, all_max, peaks, steps=3):
+    """Config 3's kernel: S = 722, dense (jdc matrix run through the DENSE recursion), logA^T streamed from L2 through
+    the 4-stage bulk-copy (TMA) ring.  One full pass of the streaming kernel -- 2072 clips = 148 SMs x 14 -- x 500 frames
+    (the named 4096 x 10,000 job is this launch repeated over waves and frame ranges: tools/bench_waves.py --config 3)."""
+    import torch
+    from viterbi_spl_b200 import ViterbiDecoder, _lib, hmm_params, synth
+    B, T, S = 2072, 500, 722
+    A, pi = hmm_params.synthetic_hmm('jdc')
+    logA_T, log_pi = hmm_params.log_params(A, pi)
+    dec = ViterbiDecoder(logA_T, log_pi, device=dev, algo='stream')
+    emis = synth.device_dense_softmax(B, T, S, seed=33, device=dev)
+    host = synth.batch('dense_softmax', 2, T, S, seed0=500)
+    emis[:2] = torch.as_tensor(host).to(dev)
+    paths = torch.empty((B, T), dtype=torch.int64, device=dev)
+    scores = torch.empty((B,), dtype=torch.float32, device=dev)
+    dec.decode_device(emis, None, paths, scores)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    n0 = _lib.launch_count()
+    e0.record()
+    for k in range(steps):
+        dec.decode_device(emis, None, paths, scores, forward_events=ev[k])
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms = all_max(e0.elapsed_time(e1) / steps)
+    fwd = all_max(statistics.mean(x.elapsed_time(y) for x, y in ev))
+    mhz = float(peaks.get('sm_max_mhz', 1965.0))
+    cells = float(B) * (T - 1) * S * S
+    out = {'workload': f'dense max-plus Viterbi, {B} clips x {T} frames x {S} states per GPU (jdc state set), logA^T '
+                       'streamed from L2 via cp.async.bulk (TMA) ring', 'algo': 'stream', 'ms_per_step': ms,
+           'forward_ms': fwd, 'steps': steps, 'value': world * B * T / (ms * 1e-3), 'unit': UNIT,
+           'gpu_launches': int(launches),
+           'roofline': {'bound': 'fp32_alu', 'kernel': 'stream_forward_kernel', 'achieved': cells / (fwd * 1e-3) / 1e12,
+                        'peak': 148 * 64 * mhz * 1e6 / 1e12, 'unit': 'Tcell/s', 'frac': cells / (fwd * 1e-3) / (148 * 64 * mhz * 1e6)}}
+    try:
+        from oracle import c_oracle
+        rp, rs = c_oracle.decode_batch_c(logA_T, log_pi, host)
+        out['parity_vs_oracle'] = bool(np.array_equal(rp, paths[:2].cpu().numpy()) and np.array_equal(rs, scores[:2].cpu().numpy()))
+    except Exception as ex:
+        out['parity_vs_oracle'] = f'oracle unavailable: {ex}'
+    return out
+
+
+def leg_strong(a, dev, rank, world, barrier, all_max, peaks):
+    """Config 5's sweep: `--strong-clips` (65,536) clips x 3000 frames x 361 states in total, sharded contiguously over
+    the ranks (65,536 / N per GPU), each shard decoded in HBM-sized waves whose emissions are generated on the device
+    on a side stream while the previous wave is decoded.  The total work is fixed, so the value at N = 1, 2, 4, 8 is the
+    STRONG-scaling curve.  `value` counts the decode calls alone (CUDA events, max over ranks); `job_value` the whole
+    job including whatever generation did not hide."""
+    import torch
+    from viterbi_spl_b200 import ViterbiDecoder, _lib, hmm_params, sharding, synth
+    from viterbi_spl_b200.waves import WaveDecoder
+    T, S = 3000, 361
+    A, pi = hmm_params.synthetic_hmm('tonet')
+    logA_T, log_pi = hmm_params.log_params(A, pi)
+    lo, hi = sharding.shard_bounds(a.strong_clips, rank, world)
+    n_mine = hi - lo
+    dec = ViterbiDecoder(logA_T, log_pi, device=dev, algo='tmem')
+    main = torch.cuda.current_stream()
+    begin, end, keep = [], [], {}
+    orig = dec.decode_device
+
+    def timed_decode(*args, **kw):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(main)
+        begin.append(ev)
+        return orig(*args, **kw)
+
+    dec.decode_device = timed_decode
+
+    def fill(start, stop, out):
+        synth.device_dense_softmax(stop - start, T, S, seed=10_000 + lo + start, device=dev, out=out)
+        return None
+
+    def sink(start, stop, paths, scores):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(main)
+        end.append(ev)
+        if start == 0 and rank == 0 and 'wd' in keep:
+            keep['clips'] = (keep['wd']._emis[0][:2].clone(), paths[:2].clone(), scores[:2].clone())
+
+    warm = WaveDecoder(dec, T, max_wave_clips=32)               # module load, first workspace
+    warm.run(min(n_mine, 32), fill, sink)
+    del warm
+    begin.clear(), end.clear()
+    dec._ws = None
+    torch.cuda.empty_cache()
+    wd = WaveDecoder(dec, T)
+    keep['wd'] = wd
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    n0 = _lib.launch_count()
+    e0.record(main)
+    waves = wd.run(n_mine, fill, sink)
+    e1.record(main)
+    barrier()
+    launches = _lib.launch_count() - n0
+    job_ms = all_max(e0.elapsed_time(e1))
+    decode_ms = all_max(sum(x.elapsed_time(y) for x, y in zip(begin, end)))
+    frames = float(a.strong_clips) * T
+    mhz = float(peaks.get('sm_max_mhz', 1965.0))
+    out = {'workload': f'{a.strong_clips} clips x {T} frames x {S} states in total, {n_mine} per GPU, dense max-plus (tmem kernel), '
+                       'waves generated on the device', 'scaling': 'strong', 'n_gpus': world,
+           'value': frames / (decode_ms * 1e-3), 'unit': UNIT, 'decode_ms': decode_ms, 'job_ms': job_ms,
+           'job_value': frames / (job_ms * 1e-3), 'waves_rank0': [y - x for x, y in waves], 'wave_quantum': wd.quantum,
+           'gpu_launches': int(launches),
+           'frac_of_fp32_maxplus_peak': frames * (T - 1) / T * S * S / (decode_ms * 1e-3) / (world * 148 * 64 * mhz * 1e6)}
+    if rank == 0 and 'clips' in keep:
+        try:
+            from oracle import c_oracle
+            E2, p2, s2 = keep['clips']
+            rp, rs = c_oracle.decode_batch_c(logA_T, log_pi, E2.cpu().numpy())
+            out['parity_vs_oracle'] = bool(np.array_equal(rp, p2.cpu().numpy()) and np.array_equal(rs, s2.cpu().numpy()))
+        except Exception as ex:
+            out['parity_vs_oracle'] = f'oracle unavailable: {ex}'
+    keep.clear()
+    return out
+
+
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the ncu capture under profiles/ (tools/ncu_summary.py traffic), but only if
+    that capture was taken from THIS build of the kernel (hash of its sources, viterbi_spl_b200.build.kernel_build_id)."""
+    from viterbi_spl_b200 import build
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'forward_traffic.json')) as fh:
+            rec = json.load(fh).get('kernels', {}).get(kernel)
+    except Exception:
+        rec = None
+    if rec is None:
+        return None, 'no ncu capture of this kernel under profiles/forward_traffic.json'
+    now = build.kernel_build_id(kernel)
+    if rec.get('build_id') != now:
+        return None, f"stale ncu capture (taken from build {rec.get('build_id')}, this is {now}): not reported"
+    return rec, None
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -251,6 +453,12 @@ def run_ours(a):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def all_max(x):
+        t_ = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_[0])
 
     B, T, S = a.clips, a.frames, a.states
     logA_T, log_pi = hmm_for(S)
@@ -354,12 +562,36 @@ def run_ours(a):
     if rank == 0:
         try:
             from oracle import c_oracle
-            nchk = min(B, 4)
+            nchk = min(B, 16)
             ref_p, ref_s = c_oracle.decode_batch_c(logA_T, log_pi, emis[:nchk].cpu().numpy())
             parity = bool(np.array_equal(ref_p, paths[:nchk].cpu().numpy()) and
                           np.array_equal(ref_s, scores[:nchk].cpu().numpy()))
         except Exception as ex:   # the oracle is test infrastructure; its absence must not break the bench
             parity = f'oracle unavailable: {ex}'
+
+    # ---- the other configurations of BASELINE.json at their named sizes (every rank takes part) -----------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    extras = {}
+    algo_res = dec.algo if dec.algo else _lib.load().vit_select_algo(B, T, S)
+    structure_kind = int(dec.structure.kind)
+    if not a.no_extras:
+        del dec, emis, paths, scores
+        torch.cuda.empty_cache()
+        for name, fn in (('forward_backward', lambda: leg_forward_backward(dev, world, barrier, all_max, peaks)),
+                         ('cfg3_stream', lambda: leg_cfg3_stream(dev, world, barrier, all_max, peaks)),
+                         ('strong', lambda: leg_strong(a, dev, rank, world, barrier, all_max, peaks))):
+            try:
+                extras[name] = fn()
+            except Exception as ex:           # an extra leg must not take the headline down with it
+                if world > 1:
+                    raise
+                extras[name] = {'error': f'{type(ex).__name__}: {ex}'}
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -367,34 +599,34 @@ def run_ours(a):
         return
 
     # ---- roofline (forward kernel) ------------------------------------------------------------------------------
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
-            peaks = json.load(fh)
-    except Exception:
-        pass
     sm_mhz_peak = float(peaks.get('sm_max_mhz', 1965.0))
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured' if peaks else 'fallback'
     cells = float(B) * (T - 1) * S * S                      # cells = sum_b (T_b - 1) S^2, 1 add + 1 max each
     cells_per_s = cells / (fwd_ms * 1e-3)
     alu_peak = 148 * 64 * sm_mhz_peak * 1e6                 # N_SM x 128 lanes x f / 2 instr per cell
-    algo_bytes = float(B) * T * S * 8                       # emissions in (4 B) + delta history out (4 B) per state-frame
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'forward_traffic.json')) as fh:
-            traffic = json.load(fh).get('dram_bytes_per_launch')
-    except Exception:
-        pass
-    algo_res = dec.algo if dec.algo else _lib.load().vit_select_algo(B, T, S)
+    # algorithmic HBM bytes per launch: SURVEY 8(d) counts 6 S per state-frame (emissions 4 B in + uint16 backpointers
+    # out); this kernel writes the fp32 delta history instead (4 B: index tracking in the hot loop costs 2.7x the cells/clk,
+    # profiles/r01_microbench_pipes.jsonl) = 8 S -- both stated, `traffic_ratio` is against SURVEY's definition
+    algo_bytes_survey = float(B) * T * S * 6
+    algo_bytes = float(B) * T * S * 8
     algo_name = {1: 'backpointer', 2: 'cluster', 3: 'tmem', 4: 'banded', 5: 'stream'}.get(algo_res, str(algo_res))
     kernel_name = {1: 'bp_forward_kernel', 2: 'cluster_forward_kernel', 3: 'tmem_forward_kernel',
                    4: 'banded_forward_kernel', 5: 'stream_forward_kernel'}.get(algo_res, '?')
+    rec, traffic_note = measured_traffic(kernel_name)
+    traffic = None
+    if rec is not None:
+        # the capture's launch shape may differ in clips/frames from the timed one: traffic is linear in state-frames
+        traffic = float(rec['dram_bytes_per_launch']) * (float(B) * T * S) / (float(rec['clips']) * rec['frames'] * rec['states'])
     roofline = {'bound': 'fp32_alu', 'kernel': kernel_name, 'achieved': cells_per_s / 1e12,
                 'peak': alu_peak / 1e12, 'unit': 'Tcell/s', 'frac': cells_per_s / alu_peak,
                 'peak_definition': f'148 SMs x 64 cells/clk (FADD+FMNMX, 2 issue slots per cell) x {sm_mhz_peak:.0f} MHz '
                                    f'({peak_src} sm_max_mhz)',
-                'kernel_ms': fwd_ms, 'kernel_share_of_step': fwd_ms / ms_per_step, 'traffic': traffic}
+                'kernel_ms': fwd_ms, 'kernel_share_of_step': fwd_ms / ms_per_step, 'traffic': traffic,
+                'algorithmic_bytes': {'survey_6S_uint16_backpointers': algo_bytes_survey, 'kernel_8S_fp32_delta_history': algo_bytes},
+                'traffic_ratio': (traffic / algo_bytes_survey) if traffic else None,
+                'traffic_source': ({'ncu_capture': rec.get('source'), 'build_id': rec.get('build_id'),
+                                    'capture_shape': [rec['clips'], rec['frames'], rec['states']]} if rec else traffic_note)}
     roofline_hbm = {'bound': 'hbm', 'achieved': algo_bytes / (fwd_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                     'frac': algo_bytes / (fwd_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': traffic,
                     'note': f'{peak_src} copy bandwidth; the kernel is FP32-issue bound, not HBM bound'}
@@ -403,16 +635,15 @@ def run_ours(a):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(a), 'clips_per_gpu': B, 'frames': T, 'states': S,
-                   'algo': algo_name,
-                   'l2': 'inputs (4.4 GB emissions per step) are far larger than the 126 MB L2',
-                   'parallelism': f'{world} x independent clip shards, no data-path collective',
-                   'host_numa_binding': numa_cpus},
+        'config': shared_config(a),
+        'details': {'algo': algo_name, 'parallelism': f'{world} x independent clip shards, no data-path collective',
+                    'host_numa_binding': numa_cpus},
         'roofline': roofline, 'roofline_hbm': roofline_hbm,
         'structured_fast_path': structured, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'parity_vs_oracle': parity,
     }
     if cpu is not None:
         line['cpu_baseline'] = cpu
+    line.update(extras)
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)

@@ -45,10 +45,11 @@ typedef enum vit_status {
 typedef enum vit_algo {
   VIT_ALGO_AUTO = 0,
   /* generic kernel: one CTA per clip, warp-shuffle (value,index) argmax, uint16 backpointer table in the
-   * workspace, one-thread-per-clip backtrace.  Any S <= 65535. */
+   * workspace, one-thread-per-clip backtrace.  Any S <= 29,056 (two delta rows per clip in shared memory; larger S gives
+   * VIT_ERR_UNSUPPORTED_ALGO from vit_select_algo / vit_workspace_bytes / vit_decode_f32 alike). */
   VIT_ALGO_BACKPOINTER = 1,
   /* persistent thread-block-cluster kernel: logA^T column-sharded and resident in shared memory, delta exchanged
-   * through distributed shared memory, register-tiled FADD2/FMNMX3 max-plus, delta history (fp32) in the workspace
+   * through distributed shared memory, register-tiled FADD + FMNMX3 (3-input max) max-plus, delta history (fp32) in the workspace
    * and the argmax resolved lazily by the backtrace only along the decoded path (bit-identical result). */
   VIT_ALGO_CLUSTER = 2,
   /* the throughput path: as VIT_ALGO_CLUSTER, but the resident logA^T shard lives in TENSOR MEMORY (tcgen05.ld into
@@ -88,7 +89,7 @@ typedef struct vit_decode_opts {
   float* d_delta;            /* [B][T_max][S] out: the reference's T1 table (imm/tf_viterbi.py:91,94,100). */
   void* ev_forward_begin;    /* optional cudaEvent_t recorded on `stream` right before the forward (recursion) kernel */
   void* ev_forward_end;      /* optional cudaEvent_t recorded right after it (bench.py times the kernel with these) */
-  /* Frame range (VIT_ALGO_TMEM and VIT_ALGO_BANDED): run the recursion over frames [frame_begin, frame_end) only; frame_end = 0
+  /* Frame range (VIT_ALGO_TMEM, VIT_ALGO_STREAM and VIT_ALGO_BANDED): run the recursion over frames [frame_begin, frame_end) only; frame_end = 0
    * means T_max.  A range with frame_begin > 0 resumes from the delta history that an earlier call on the SAME
    * workspace left behind, so a host can upload a long batch in time slabs and overlap each copy with the recursion
    * over the previous slab.  skip_backtrace != 0 leaves d_paths / d_scores untouched (all but the last slab). */

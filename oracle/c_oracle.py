@@ -35,6 +35,8 @@ def lib():
         L.vit_oracle_decode_batch_f32.argtypes = [f32p, f32p, f32p, i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                   i64p, f32p, ctypes.c_int]
         L.vit_oracle_max_threads.restype = ctypes.c_int
+        L.vit_oracle_decode_long_f32.restype = ctypes.c_int
+        L.vit_oracle_decode_long_f32.argtypes = [f32p, f32p, f32p, ctypes.c_int, ctypes.c_int, i64p, f32p, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -78,6 +80,22 @@ def decode_batch_c(logA_T, log_pi, log_emis, lengths=None, nthreads=0):
                                            _p(paths, ctypes.c_int64), _p(scores, ctypes.c_float), int(nthreads))
     assert rc == 0, rc
     return paths, scores
+
+
+def viterbi_log_long_c(logA_T, log_pi, log_emis_ts, nthreads=0):
+    """One LONG clip, emissions [T, S], the targets of every step split over `nthreads` threads (0 = all cores);
+    bit-identical to viterbi_log_c.  Returns (states int64[T], score float32)."""
+    A = np.require(logA_T, np.float32, ['C'])
+    pi = np.require(log_pi, np.float32, ['C'])
+    E = np.require(log_emis_ts, np.float32, ['C'])
+    T, S = E.shape
+    assert A.shape == (S, S) and pi.shape == (S,)
+    states = np.empty([T], np.int64)
+    score = np.zeros([1], np.float32)
+    rc = lib().vit_oracle_decode_long_f32(_p(A, ctypes.c_float), _p(pi, ctypes.c_float), _p(E, ctypes.c_float), T, S,
+                                          _p(states, ctypes.c_int64), _p(score, ctypes.c_float), int(nthreads))
+    assert rc == 0, rc
+    return states, score[0]
 
 
 def max_threads():

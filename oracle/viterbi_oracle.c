@@ -163,3 +163,96 @@ int vit_oracle_decode_batch_f32(const float* logA_T, const float* log_pi, const 
   free(th);
   return J.rc;
 }
+
+/*
+ * ONE long sequence, the same recursion with the S targets of every step split over `nthreads` POSIX threads (a
+ * spin barrier per step): the single 1,000,000-frame sequence of BASELINE.json's config 5 takes ~200 s through
+ * vit_oracle_decode_f32 on one core, ~15 s this way on 16.  Each (t, j) cell is computed by exactly the same
+ * first_argmax_add as above -- threads only partition j -- so the result is bit-identical to the single-threaded
+ * function (tests/test_oracle.py asserts it).  Only two T1 rows are kept (the reference's full T1 table is never read
+ * again after the step that consumes it, imm/tf_viterbi.py:97-107); T2 is uint16 (S <= 65535).
+ */
+typedef struct {
+  const float* logA_T; const float* log_emis; int T, S, nthreads;
+  float* rows;        /* [2][S] */
+  uint16_t* T2;       /* [T][S] */
+  int count; int sense;
+} vit_long_job;
+
+typedef struct { vit_long_job* J; int tid; } vit_long_arg;
+
+static inline void vit_spin_barrier(vit_long_job* J, int* local_sense) {
+  *local_sense = !*local_sense;
+  if (__atomic_add_fetch(&J->count, 1, __ATOMIC_ACQ_REL) == J->nthreads) {
+    __atomic_store_n(&J->count, 0, __ATOMIC_RELAXED);
+    __atomic_store_n(&J->sense, *local_sense, __ATOMIC_RELEASE);
+  } else {
+    while (__atomic_load_n(&J->sense, __ATOMIC_ACQUIRE) != *local_sense) __builtin_ia32_pause();
+  }
+}
+
+static void* vit_long_worker(void* p) {
+  vit_long_arg* a = (vit_long_arg*)p;
+  vit_long_job* J = a->J;
+  const int S = J->S;
+  const int j0 = (int)((long long)S * a->tid / J->nthreads), j1 = (int)((long long)S * (a->tid + 1) / J->nthreads);
+  float* tmp = (float*)malloc((size_t)S * sizeof(float));
+  int sense = 0;
+  for (int t = 1; t < J->T; ++t) {
+    const float* prev = J->rows + (size_t)((t - 1) & 1) * S;
+    float* cur = J->rows + (size_t)(t & 1) * S;
+    const float* e = J->log_emis + (size_t)t * S;
+    uint16_t* bp = J->T2 + (size_t)t * S;
+    for (int j = j0; j < j1; ++j) {
+      float best;
+      bp[j] = (uint16_t)first_argmax_add(prev, J->logA_T + (size_t)j * S, S, tmp, &best);
+      cur[j] = best + e[j];
+    }
+    vit_spin_barrier(J, &sense);
+  }
+  free(tmp);
+  return NULL;
+}
+
+int vit_oracle_decode_long_f32(const float* logA_T, const float* log_pi, const float* log_emis, int T, int S,
+                               int64_t* states, float* score, int nthreads) {
+  if (!logA_T || !log_pi || !log_emis || !states || T < 1 || S < 1 || S > 65535) return VIT_ORACLE_EINVAL;
+  if (nthreads <= 0) nthreads = vit_oracle_max_threads();
+  if (nthreads > S) nthreads = S;
+  if (nthreads > 64) nthreads = 64;
+  vit_long_job J = {logA_T, log_emis, T, S, nthreads, NULL, NULL, 0, 0};
+  J.rows = (float*)malloc((size_t)2 * S * sizeof(float));
+  J.T2 = (uint16_t*)malloc((size_t)T * S * sizeof(uint16_t));
+  if (!J.rows || !J.T2) { free(J.rows); free(J.T2); return VIT_ORACLE_ENOMEM; }
+  for (int j = 0; j < S; ++j) J.rows[j] = log_pi[j] + log_emis[j];          /* :94 */
+  pthread_t th[64];
+  vit_long_arg args[64];
+  int started = 0;
+  for (int i = 1; i < nthreads; ++i) {
+    args[i].J = &J; args[i].tid = i;
+    if (pthread_create(&th[i], NULL, vit_long_worker, &args[i]) != 0) break;
+    ++started;
+  }
+  if (started != nthreads - 1) {            /* could not start them all: the barrier would never fill */
+    J.nthreads = 1;                          /* (threads already started would spin; none were: creation is all-or-nothing here) */
+    if (started > 0) { free(J.rows); free(J.T2); return VIT_ORACLE_ENOMEM; }
+  }
+  args[0].J = &J; args[0].tid = 0;
+  vit_long_worker(&args[0]);
+  for (int i = 1; i <= started; ++i) pthread_join(th[i], NULL);
+  {
+    const float* last = J.rows + (size_t)((T - 1) & 1) * S;                   /* :103-107 */
+    int32_t s = 0;
+    float m = last[0];
+    for (int j = 1; j < S; ++j) if (last[j] > m) { m = last[j]; s = j; }
+    if (score) *score = m;
+    states[T - 1] = s;
+    for (int t = T - 2; t >= 0; --t) {
+      s = J.T2[(size_t)(t + 1) * S + s];
+      states[t] = s;
+    }
+  }
+  free(J.rows);
+  free(J.T2);
+  return VIT_ORACLE_OK;
+}

@@ -119,3 +119,27 @@ def test_device_api_and_error_codes(FB, cuda_lib):
     assert cuda_lib.vit_fb_workspace_bytes(4, 30, 50, ctypes.byref(n)) == 0 and n.value > 0
     assert cuda_lib.vit_fb_workspace_bytes(4, 30, 5000, ctypes.byref(n)) == -4
     assert cuda_lib.vit_fb_workspace_bytes(4, 0, 50, ctypes.byref(n)) == -1
+
+
+def test_impossible_observation_sequence_gives_zero_gamma_not_nan(FB):
+    """A clip whose likelihoods make every path impossible from frame 7 on (the library's own emission builder writes
+    exact zeros for non-peak bins, and off-band transitions are exactly 0): the normaliser reaches 0.  gamma must be 0 for
+    that clip (never NaN), log L = -inf, and the other clips of the batch are unaffected."""
+    S, T = 40, 16
+    rng = np.random.default_rng(5)
+    A = np.zeros((S, S), np.float32)
+    for d in (-1, 0, 1):
+        i = np.arange(max(0, -d), min(S, S - d))
+        A[i, i + d] = 1.0
+    A /= A.sum(1, keepdims=True)                                  # band +-1: state 0 cannot reach state 30 in one step
+    pi = np.full(S, 1.0 / S, np.float32)
+    lik = (rng.random((3, T, S)) + 0.1).astype(np.float32)
+    lik[1, 6] = 0
+    lik[1, 6, 0] = 1.0                                            # frame 6: only state 0 ...
+    lik[1, 7] = 0
+    lik[1, 7, 30] = 1.0                                           # ... frame 7: only state 30 -> probability 0
+    g, ll = FB(A, pi).run_host(lik)
+    assert not np.isnan(g).any()
+    assert np.all(g[1] == 0) and ll[1] == -np.inf
+    want_g, want_ll = fb_oracle.forward_backward_batch_np(A, pi, lik[[0, 2]])
+    assert np.abs(g[[0, 2]] - want_g).max() <= GAMMA_ATOL and np.allclose(ll[[0, 2]], want_ll, rtol=LOGLIK_RTOL)

@@ -112,3 +112,13 @@ def test_wave_planner():
     assert plan_waves(5, 100, 10 ** 6, quantum=4, max_wave_clips=2) == [(0, 2), (2, 4), (4, 5)]
     with pytest.raises(MemoryError):
         plan_waves(3, 1000, 999)
+
+
+def test_host_paths_validate_clip_lengths():
+    """decode_host / run_host / MelodyPipeline.evaluate still have the lengths on the host: a value outside [0, T] would
+    make the kernels read and write past a clip's rows, so it is refused before anything is uploaded."""
+    from viterbi_spl_b200.decoder import checked_lengths
+    assert checked_lengths([0, 5, 3], 3, 5).dtype == np.int32
+    for bad in ([0, 6, 3], [-1, 2, 2], [1, 2], np.zeros((3, 1), np.int32)):
+        with pytest.raises(ValueError):
+            checked_lengths(bad, 3, 5)

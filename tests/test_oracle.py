@@ -150,3 +150,19 @@ def test_post_decode_restatement_hand_checked():
     assert np.allclose(est, [23.7, -25.6, 23.6 + 63.7], atol=1e-5)
     assert c == dict(gt_voiced=2, gt_unvoiced=1, correct_voiced=2, incorrect_voiced=0, correct_unvoiced=1,
                      correct_pitches_wide=1, correct_pitches_strict=1, correct_chromas_wide=2, correct_chromas_strict=2)
+
+
+def test_long_sequence_oracle_equals_the_single_threaded_one(oracle_c):
+    """vit_oracle_decode_long_f32 (targets of a step split over threads; what checks the 1,000,000-frame case) is
+    bit-identical to the plain C restatement, for any thread count."""
+    from viterbi_spl_b200 import hmm_params
+    A, pi = hmm_params.synthetic_hmm('dcnet')
+    logA_T, log_pi = hmm_params.log_params(A, pi)
+    E = synth.sparse_peaks(700, 321, seed=9)
+    want = c_oracle.viterbi_log_c(logA_T, log_pi, E)
+    for n in (1, 3, 8, 0):
+        got = c_oracle.viterbi_log_long_c(logA_T, log_pi, E, nthreads=n)
+        assert np.array_equal(got[0], want[0]) and got[1] == want[1], n
+    A, pi = synth.dyadic_hmm(5, seed=1, coarse=True)
+    E = synth.tie_stress((40, 5), 2)
+    assert np.array_equal(c_oracle.viterbi_log_long_c(A, pi, E, nthreads=8)[0], c_oracle.viterbi_log_c(A, pi, E)[0])

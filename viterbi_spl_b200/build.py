@@ -18,6 +18,31 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '--compiler-options', '-fPIC', '-shared', '-Xptxas', '-v']
 
 
+# the sources a kernel's machine code depends on: their hash is the "build id" that ties an ncu capture under profiles/
+# (DRAM traffic per launch) to the library bench.py is timing -- a capture of an older kernel is refused, not reported
+KERNEL_SOURCES = {
+    'tmem_forward_kernel': ['vit_tmem.cu', 'vit_tmem.cuh', 'vit_common.cuh'],
+    'stream_forward_kernel': ['vit_stream.cu', 'vit_tmem.cuh', 'vit_common.cuh'],
+    'cluster_forward_kernel': ['vit_cluster.cu', 'vit_common.cuh'],
+    'bp_forward_kernel': ['vit_backpointer.cu', 'vit_common.cuh'],
+    'banded_forward_kernel': ['vit_banded.cu', 'vit_tmem.cuh', 'vit_common.cuh'],
+    'wide_forward_kernel': ['vit_banded_wide.cu', 'vit_tmem.cuh', 'vit_common.cuh'],
+    'fb_tc_pass_kernel': ['vit_fb_tc.cu', 'vit_common.cuh'],
+    'fb_pass_kernel': ['vit_fb.cu', 'vit_tmem.cuh', 'vit_common.cuh'],
+    'emissions_reg_kernel': ['vit_emis.cu', 'vit_common.cuh'],
+}
+
+
+def kernel_build_id(kernel):
+    """16 hex digits identifying the build of one kernel: sha256 over its source files and the nvcc flags."""
+    import hashlib
+    h = hashlib.sha256(' '.join(NVCC_FLAGS).encode())
+    for name in KERNEL_SOURCES[kernel]:
+        with open(os.path.join(CSRC, name), 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def nvcc():
     exe = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     if not os.path.exists(exe):

@@ -29,6 +29,7 @@ int cuda_fail(cudaError_t e) {
 
 // vit_backpointer.cu
 size_t bp_workspace_bytes(int B, int T_max, int S, bool external_bp);
+bool bp_supported(int S);
 int bp_decode(const float* logA_T, const float* log_pi, const float* log_emis, const int32_t* lengths, int B,
               int T_max, int S, void* workspace, size_t workspace_bytes, int64_t* paths, float* scores,
               uint16_t* bp_out, float* delta_out, cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t stream);
@@ -125,13 +126,14 @@ static int auto_dense_algo(int B, int S) {
     }
     return VIT_ALGO_STREAM;
   }
-  return tmem_supported(S) ? VIT_ALGO_TMEM : (cluster_supported(S) ? VIT_ALGO_CLUSTER : VIT_ALGO_BACKPOINTER);
+  if (tmem_supported(S)) return VIT_ALGO_TMEM;
+  if (cluster_supported(S)) return VIT_ALGO_CLUSTER;
+  return bp_supported(S) ? (int)VIT_ALGO_BACKPOINTER : (int)VIT_ERR_UNSUPPORTED_ALGO;
 }
 
 static int resolve_algo(int algo, int S, bool want_bp, int B = 0) {
-  if (want_bp) return VIT_ALGO_BACKPOINTER;
+  if (want_bp || algo == VIT_ALGO_BACKPOINTER) return bp_supported(S) ? (int)VIT_ALGO_BACKPOINTER : (int)VIT_ERR_UNSUPPORTED_ALGO;
   if (algo == VIT_ALGO_AUTO) return auto_dense_algo(B, S);
-  if (algo == VIT_ALGO_BACKPOINTER) return algo;
   if (algo == VIT_ALGO_CLUSTER) return cluster_supported(S) ? algo : VIT_ERR_UNSUPPORTED_ALGO;
   if (algo == VIT_ALGO_TMEM) return tmem_supported(S) ? algo : VIT_ERR_UNSUPPORTED_ALGO;
   if (algo == VIT_ALGO_STREAM) return stream_supported(S) ? algo : VIT_ERR_UNSUPPORTED_ALGO;
@@ -245,7 +247,6 @@ int vit_decode_f32_ex(const float* d_logA_T, const float* d_log_pi, const float*
     return banded_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, structure, d_workspace,
                          workspace_bytes, d_paths, d_scores, delta_out, f_begin, f_end, !skip_bt, ev0, ev1, st);
   if (algo == VIT_ALGO_TMEM) {
-    // bit 3 of the S check: the shared lazy-argmax backtrace handles S <= 384, which is also the TMEM plan's limit
     return tmem_decode(d_logA_T, d_log_pi, d_log_emis, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_paths,
                        d_scores, delta_out, f_begin, f_end, !skip_bt, ev0, ev1, st);
   }

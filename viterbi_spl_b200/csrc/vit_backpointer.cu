@@ -126,6 +126,10 @@ __global__ void bp_backtrace_kernel(const uint16_t* __restrict__ bp, const int32
   }
 }
 
+// The forward kernel keeps two delta rows of every clip of its CTA in shared memory: S <= 227 KB / 8 B = 29,056 states
+// with one clip per CTA (far beyond any pitch-bin state set; uint16 backpointers would allow 65,535).
+bool bp_supported(int S) { return S >= 1 && (size_t)2 * S * sizeof(float) <= (size_t)227 * 1024; }
+
 size_t bp_workspace_bytes(int B, int T_max, int S, bool external_bp) {
   size_t bytes = align_up((size_t)(B > 0 ? B : 1) * sizeof(int32_t), 256);      // last_state
   if (!external_bp) bytes += align_up((size_t)B * T_max * S * sizeof(uint16_t), 256);
@@ -156,6 +160,7 @@ int bp_decode(const float* logA_T, const float* log_pi, const float* log_emis, c
               int64_t* paths, float* scores, uint16_t* bp_out, float* delta_out, cudaEvent_t ev0, cudaEvent_t ev1,
               cudaStream_t stream) {
   if (S > 65535) return VIT_ERR_STATES_TOO_MANY;
+  if (!bp_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;
   if (workspace_bytes < bp_workspace_bytes(B, T_max, S, bp_out != nullptr)) return VIT_ERR_WORKSPACE_TOO_SMALL;
   if (B == 0) return VIT_OK;
   char* ws = (char*)workspace;

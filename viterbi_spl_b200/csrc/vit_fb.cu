@@ -161,7 +161,9 @@ fb_pass_kernel(const float* __restrict__ packedT, const float* __restrict__ pack
 
       float acc[NPAD];
       float inv0 = 1.f, inv1 = 1.f;        // scale applied to the matrix-vector product of my two clips
-      const float rc0 = 1.f / c_t0, rc1 = 1.f / c_t1;
+      // (guarded like the forward pass: an impossible observation sequence -- a normaliser of 0 -- gives gamma = 0 from
+      // that frame on and log L = -inf, never inf * 0 = NaN)
+      const float rc0 = c_t0 > 0.f ? 1.f / c_t0 : 0.f, rc1 = c_t1 > 0.f ? 1.f / c_t1 : 0.f;
       if (first) {
 #pragma unroll
         for (int k = 0; k < 2 * NJ; ++k) acc[k] = 0.f;
@@ -183,8 +185,8 @@ fb_pass_kernel(const float* __restrict__ packedT, const float* __restrict__ pack
             if (has_b1 && t - 1 < len1 && seq0 + b0 + 1 < B) cnorm[(size_t)(seq0 + b0 + 1) * T_max + t - 1] = c1;
           }
         } else {
-          inv0 = 1.f / c_n0;
-          inv1 = 1.f / c_n1;
+          inv0 = c_n0 > 0.f ? 1.f / c_n0 : 0.f;
+          inv1 = c_n1 > 0.f ? 1.f / c_n1 : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < NPAD; ++i) acc[i] = 0.f;

@@ -298,7 +298,10 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
         if (BWD && tid < 2 * cN) {
           // 1 / c_t (threads 0-31) and 1 / c_{t+1} (32-63) of the 32 clips: fetched while the MMAs run
           const int n = tid & (cN - 1), tt = t + (tid >> 5);
-          s_c[tid >> 5][n] = (tt < s_len[n]) ? 1.f / cnorm[(size_t)(seq0 + n) * T_max + tt] : 1.f;
+          // (guarded like the forward pass: a normaliser of 0 -- an impossible observation sequence -- gives gamma = 0,
+          // not inf * 0 = NaN; log L is then -inf)
+          const float cv = (tt < s_len[n]) ? cnorm[(size_t)(seq0 + n) * T_max + tt] : 1.f;
+          s_c[tid >> 5][n] = cv > 0.f ? 1.f / cv : 0.f;
         }
         VIT_STAMP(2);
         if (!(dev & 4)) { mbar_wait_cta(smem_u32(&s_bar[2]), n_mma & 1u); ++n_mma; }
@@ -328,7 +331,10 @@ fb_tc_pass_kernel(const uint32_t* __restrict__ packed, const float* __restrict__
           }
         }
       }
-      if (BWD && first && tid < cN) s_c[0][tid] = (t < s_len[tid]) ? 1.f / cnorm[(size_t)(seq0 + tid) * T_max + t] : 1.f;
+      if (BWD && first && tid < cN) {
+        const float cv = (t < s_len[tid]) ? cnorm[(size_t)(seq0 + tid) * T_max + t] : 1.f;
+        s_c[0][tid] = cv > 0.f ? 1.f / cv : 0.f;
+      }
       VIT_STAMP(4);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();                                    // s_c visible; D fully read before the next MMA batch

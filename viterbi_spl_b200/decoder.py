@@ -21,6 +21,18 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def checked_lengths(lengths, B, T):
+    """Host-side clip lengths -> int32 [B], each in [0, T].  The kernels trust the lengths they are given (a device
+    pointer cannot be validated by the C ABI): a larger value would read emissions and write the delta history past the
+    clip's rows, so every path that still has the lengths on the host checks them here."""
+    L = np.asarray(lengths)
+    if L.shape != (B,):
+        raise ValueError(f'lengths must have shape ({B},), got {L.shape}')
+    if L.size and (L.min() < 0 or L.max() > T):
+        raise ValueError(f'clip lengths must be in [0, {T}]; got min {L.min()}, max {L.max()}')
+    return np.ascontiguousarray(L, np.int32)
+
+
 class ViterbiDecoder:
     """Holds the HMM parameters on one GPU plus a reusable workspace; decodes batches of clips.
 
@@ -157,7 +169,7 @@ class ViterbiDecoder:
                 src.copy_(E)
             dL = None
             if lengths is not None:
-                dL = torch.as_tensor(np.asarray(lengths, np.int32)).to(self.device)
+                dL = torch.as_tensor(checked_lengths(lengths, B, T)).to(self.device)
             if slab_frames is None:
                 slab_frames = T if B * T * S * 4 < (64 << 20) else max(64, -(-T // 16))
             if slab_frames >= T or B == 0 or not self.supports_frame_slabs():
@@ -255,6 +267,11 @@ class PipelinedDecoder:
             main.wait_event(self._done[slot])      # the forward about to run overwrites that slot's history
         out = self.dec.decode_device(log_emis, lengths, paths, scores, forward_events=forward_events,
                                      backtrace_stream=self.bt_stream, workspace_slot=slot)
+        # the backtrace reads the lengths and the workspace and writes paths / scores on bt_stream: tell the caching
+        # allocator, or a block the caller drops before finish() could be handed out while the walk still uses it
+        for t in (out[0], out[1], lengths, self.dec._ws.get(slot)):
+            if t is not None:
+                t.record_stream(self.bt_stream)
         ev = torch.cuda.Event()
         ev.record(self.bt_stream)
         self._done[slot] = ev

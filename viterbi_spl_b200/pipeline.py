@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib, hmm_params
-from .decoder import ViterbiDecoder
+from .decoder import ViterbiDecoder, checked_lengths
 
 SOFTMAX, SHAUN = 0, 1
 
@@ -130,7 +130,10 @@ class MelodyPipeline:
         logits = torch.as_tensor(logits).to(self.device, torch.float32).contiguous()
         assert logits.ndim == 3
         if lengths is not None:
-            lengths = torch.as_tensor(lengths).to(self.device, torch.int32).contiguous()
+            if not (torch.is_tensor(lengths) and lengths.is_cuda):
+                lengths = torch.as_tensor(checked_lengths(torch.as_tensor(lengths).numpy() if torch.is_tensor(lengths) else lengths,
+                                                          logits.shape[0], logits.shape[1]))
+            lengths = lengths.to(self.device, torch.int32).contiguous()
         voiced, bins = self(logits, lengths)
         off = 1 if self.model == SOFTMAX else 0
         est, counters = melody_stats_device(logits, torch.as_tensor(ref_notes), bins, voiced, lengths, self.n_bins, off,

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .decoder import checked_lengths
 
 
 def _ptr(t):
@@ -65,6 +66,6 @@ class ForwardBackward:
     def run_host(self, lik, lengths=None):
         """NumPy in, NumPy out."""
         E = torch.as_tensor(np.ascontiguousarray(lik, np.float32)).to(self.device)
-        dL = None if lengths is None else torch.as_tensor(np.asarray(lengths, np.int32)).to(self.device)
+        dL = None if lengths is None else torch.as_tensor(checked_lengths(lengths, E.shape[0], E.shape[1])).to(self.device)
         g, ll = self.run_device(E, dL)
         return g.cpu().numpy(), ll.cpu().numpy()
