@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libvit_b200.so')
+# (VIT_B200_LIB: a development build of the same library, e.g. one compiled with -DVIT_FB_STAMPS)
+LIB_PATH = os.environ.get('VIT_B200_LIB') or os.path.join(_HERE, 'libvit_b200.so')
 
 VIT_OK = 0
 ALGO_AUTO, ALGO_BACKPOINTER, ALGO_CLUSTER, ALGO_TMEM, ALGO_BANDED, ALGO_STREAM = 0, 1, 2, 3, 4, 5
