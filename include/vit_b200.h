@@ -215,8 +215,9 @@ int vit_voiced_bins(const int64_t* d_states, long long n, int n_bins, uint8_t* d
  *   d_lengths  [B] or NULL;  frames past a clip's length count nowhere and get est_note 0
  *   d_est_notes[B][T] out: +note where decoded voiced, -note where not (:2975)
  *   d_counters [B][VIT_MELODY_COUNTERS] int64 out (zeroed by the call)
- * The reference's version is TensorFlow (absent from this image): float32 like it, checked against a NumPy
- * restatement (oracle/post_oracle.py) to 1e-5 on notes -- parity unpinned for this entry point.
+ * The reference's version is TensorFlow (absent from this image): float32 like it, checked to 1e-5 on notes against
+ * goldens produced by executing the reference's own function text on a NumPy-backed stand-in for its TensorFlow ops
+ * (tests/golden/melody_stats.npz; oracle/ref_loader.py dcnet_melody_stats).
  */
 #define VIT_MELODY_COUNTERS 9
 int vit_melody_stats_f32(const float* d_logits, int logit_stride, int logit_offset, const float* d_ref_notes,

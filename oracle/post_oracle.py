@@ -1,9 +1,13 @@
 """TEST INFRASTRUCTURE ONLY -- NumPy restatement of the reference's post-decode statistics step.
 
-PARITY UNPINNED: the reference's version is TensorFlow (`MetricsInference.viterbi_update_states_tf_fn`,
+The reference's version is TensorFlow (`MetricsInference.viterbi_update_states_tf_fn`,
 dcnet/softmax_viterbi.py:2923-2979, calling `MetricsBase.est_notes_fn`, dcnet/main.py:1911-1934) and TensorFlow is not
-in this image, so no golden vector could be produced by executing it; this file follows those lines one by one in
-float32.  Only tests/ may import it.
+in this image; this file follows those lines one by one in float32.  PARITY PINNED (round 2): the reference's own
+function text is executed on a NumPy-backed stand-in for the TensorFlow ops it calls (oracle/ref_loader.py
+`dcnet_melody_stats`), its outputs are committed as tests/golden/melody_stats.npz, and tests/test_oracle.py checks this
+restatement against them and against the live reference function (bit-equal here).  What stays outside the pin is
+TensorFlow's own float32 `sigmoid` kernel (1 / (1 + exp(-x)) here), hence the 1e-5 tolerance on notes.  Only tests/ may
+import this file.
 """
 import numpy as np
 

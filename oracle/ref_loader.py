@@ -206,6 +206,76 @@ class FakeTF:
         return np.argmax(np.asarray(x), axis=axis).astype(output_type).view(_NPTensor)
 
 
+class _NPMath:
+    @staticmethod
+    def count_nonzero(x, dtype=np.int64):
+        return np.asarray(np.count_nonzero(np.asarray(x)), dtype).view(_NPTensor)
+
+
+def _np_tensor(x, dtype=None):
+    return np.asarray(x, dtype).view(_NPTensor)
+
+
+class FakeTFStats(FakeTF):
+    """FakeTF plus the float32 element-wise / reduction ops of ``MetricsInference.viterbi_update_states_tf_fn`` and
+    ``MetricsBase.est_notes_fn`` / ``octave`` / ``count_nonzero_fn`` (dcnet/softmax_viterbi.py:1919-1958, 2923-2979), each
+    mapped to the NumPy ufunc of the same name on float32 arrays -- enough to EXECUTE those reference functions.
+    (``tf.sigmoid`` is 1 / (1 + exp(-x)) in float32 here; TensorFlow's kernel may differ in the last ulp, which is why the
+    product is held to 1e-5 on notes and the counters may differ on frames within 2e-5 of a threshold.)"""
+    bool = np.bool_
+    int64 = np.int64
+    math = _NPMath
+
+    convert_to_tensor = staticmethod(lambda x, dtype=None: _np_tensor(x, dtype))
+    constant = staticmethod(lambda x, dtype=None: _np_tensor(x, dtype))
+    cast = staticmethod(lambda x, dtype: _np_tensor(np.asarray(x).astype(dtype)))
+    logical_not = staticmethod(lambda x: np.logical_not(x).view(_NPTensor))
+    logical_and = staticmethod(lambda a, b: np.logical_and(a, b).view(_NPTensor))
+    abs = staticmethod(lambda x: np.abs(x).view(_NPTensor))
+    floor = staticmethod(lambda x: np.floor(x).view(_NPTensor))
+    maximum = staticmethod(lambda a, b: np.maximum(a, np.asarray(b, np.asarray(a).dtype)).view(_NPTensor))
+    zeros_like = staticmethod(lambda x: np.zeros_like(np.asarray(x)).view(_NPTensor))
+    where = staticmethod(lambda c, a, b: np.where(c, a, b).view(_NPTensor))
+    reduce_sum = staticmethod(lambda x, axis=None: np.sum(np.asarray(x), axis=axis, dtype=np.asarray(x).dtype).view(_NPTensor))
+    range = staticmethod(lambda n, dtype=np.int32: np.arange(n, dtype=dtype).view(_NPTensor))
+    size = staticmethod(lambda x, out_type=np.int32: np.asarray(np.asarray(x).size, out_type).view(_NPTensor))
+
+    @staticmethod
+    def sigmoid(x):
+        x = np.asarray(x, np.float32)
+        return (np.float32(1) / (np.float32(1) + np.exp(-x))).astype(np.float32).view(_NPTensor)
+
+
+def dcnet_melody_stats():
+    """(f)3: the reference's OWN ``MetricsInference.viterbi_update_states_tf_fn`` (dcnet/softmax_viterbi.py:2923-2979) with its
+    ``MetricsBase`` helpers (:1919-1958), executed on FakeTFStats.  Returns
+    ``fn(ref_notes [T] f32, logits [T, 320] f32, melody_bins [T] int32, est_voicing [T] bool) -> (est_notes_with_voicing_info
+    [T] f32, {counter name: int})`` with the counters in the names the reference's variable dictionary uses."""
+    relpath = 'dcnet/softmax_viterbi.py'
+    tf = FakeTFStats
+    note_range = (np.arange(320) / 5. + 23.6).astype(np.float32)                 # TFDataset.note_range, :428-432
+    ns = {'tf': tf, 'TFDataset': type('TFDataset', (), {'note_range': note_range})}
+    base = type('MetricsBase', (), {name: staticmethod(ref_method(relpath, 'MetricsBase', name, extra=ns))
+                                    for name in ('count_nonzero_fn', 'est_notes_fn', 'octave')})
+    ns['MetricsBase'] = base
+    update = ref_method(relpath, 'MetricsInference', 'viterbi_update_states_tf_fn', extra=ns)
+
+    class _Self:
+        def __init__(self):
+            self.values = {}
+            self.viterbi_var_dict = {'all_updated': {0: True}}
+
+        def update_melody_var_fn(self, rec_idx, l1, l2, value, viterbi=False):
+            assert viterbi
+            self.values[f'{l1}_{l2}'] = int(value)
+
+    def fn(ref_notes, logits, melody_bins, est_voicing):
+        me = _Self()
+        out = update(me, 0, ref_notes, logits, melody_bins, est_voicing)
+        return np.asarray(out, np.float32), me.values
+    return fn
+
+
 # (file, class) of every ``class Viterbi`` / ``class SoftMaxViterbi`` copy the drop-in namespaces mirror
 CLASS_COPIES = {
     ('dcnet', 'Viterbi'): 'dcnet/softmax_viterbi.py', ('dcnet', 'SoftMaxViterbi'): 'dcnet/softmax_viterbi.py',

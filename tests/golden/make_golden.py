@@ -194,9 +194,37 @@ def class_calls():
     save('class_calls.npz', **out)
 
 
+def melody_stats():
+    """8. The statistics step after the decode: the reference's OWN MetricsInference.viterbi_update_states_tf_fn +
+    MetricsBase.est_notes_fn / octave / count_nonzero_fn (dcnet/softmax_viterbi.py:1919-1958, 2923-2979), executed on
+    the NumPy-backed stand-in for the TensorFlow ops they call (oracle/ref_loader.FakeTFStats).  -> melody_stats.npz"""
+    fn = rl.dcnet_melody_stats()
+    out = {}
+    for k, (seed, T) in enumerate(((1, 300), (2, 1), (3, 129), (4, 400))):
+        rng = np.random.default_rng(seed)
+        logits = rng.normal(0, 3, (T, 320)).astype(np.float32)
+        bins = rng.integers(0, 320, T).astype(np.int32)
+        bins[:4] = np.asarray((0, 319, 1, 318))[:T]                              # window clipped at both ends of the bin range
+        voiced = rng.random(T) < 0.6
+        ref = (23.6 + bins / 5. + rng.normal(0, 0.4, T)).astype(np.float32)      # around the decoded bin: hits and misses
+        ref[rng.random(T) < 0.15] += 12.                                         # octave errors: chroma hit, pitch miss
+        ref[rng.random(T) < 0.3] = 0.                                            # unvoiced reference frames
+        est, counters = fn(ref, logits, bins, voiced)
+        out[f'c{k}_logits'], out[f'c{k}_bins'], out[f'c{k}_voiced'], out[f'c{k}_ref'] = logits, bins, voiced, ref
+        out[f'c{k}_est'] = est
+        out[f'c{k}_counters'] = np.asarray([counters[n] for n in ('gt_voiced', 'gt_unvoiced', 'voicing_correct_voiced',
+                                                                  'voicing_incorrect_voiced', 'voicing_correct_unvoiced',
+                                                                  'correct_pitches_wide', 'correct_pitches_strict',
+                                                                  'correct_chromas_wide', 'correct_chromas_strict')], np.int64)
+    out['n_cases'] = np.array(4)
+    save('melody_stats.npz', **out)
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'class_calls':
-        class_calls()
-    else:
+    which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    if which in ('all', 'main'):
         main()
+    if which in ('all', 'class_calls'):
         class_calls()
+    if which in ('all', 'melody_stats'):
+        melody_stats()

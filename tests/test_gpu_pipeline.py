@@ -168,6 +168,35 @@ def test_melody_stats_match_the_reference_restatement(pl):
         assert got['gt_voiced'] + got['gt_unvoiced'] == n
 
 
+def test_melody_stats_match_goldens_made_by_the_reference_function(pl):
+    """vit_melody_stats_f32 against the outputs of the reference's own viterbi_update_states_tf_fn / est_notes_fn
+    (tests/golden/melody_stats.npz, made by executing those functions on a NumPy-backed stand-in for their TensorFlow
+    ops): notes to 1e-5, the five voicing counters exact, the four note-threshold counters up to the frames whose note
+    lies within 2e-5 of a threshold."""
+    g = np.load(os.path.join(GOLD, 'melody_stats.npz'))
+    n_cases = int(g['n_cases'])
+    T_max = max(len(g[f'c{k}_ref']) for k in range(n_cases))
+    L = np.zeros((n_cases, T_max, 320), np.float32)
+    R = np.zeros((n_cases, T_max), np.float32)
+    Bn = np.full((n_cases, T_max), -1, np.int64)
+    V = np.zeros((n_cases, T_max), bool)
+    lengths = np.asarray([len(g[f'c{k}_ref']) for k in range(n_cases)], np.int32)
+    for k in range(n_cases):
+        n = lengths[k]
+        L[k, :n], R[k, :n], Bn[k, :n], V[k, :n] = g[f'c{k}_logits'], g[f'c{k}_ref'], g[f'c{k}_bins'], g[f'c{k}_voiced']
+    est, counters = pl.melody_stats_device(torch.as_tensor(L).cuda(), torch.as_tensor(R), torch.as_tensor(Bn),
+                                           torch.as_tensor(V), lengths)
+    est, counters = est.cpu().numpy(), counters.cpu().numpy()
+    for k in range(n_cases):
+        n = lengths[k]
+        want = g[f'c{k}_est']
+        assert np.allclose(est[k, :n], want, rtol=1e-5, atol=1e-5)
+        diff = np.abs(np.abs(want) - g[f'c{k}_ref'])
+        edge = int(np.sum(np.abs(diff - 0.5) < 2e-5) + np.sum(np.abs(np.abs(diff - np.round(diff / 12) * 12) - 0.5) < 2e-5))
+        assert np.array_equal(counters[k, :5], g[f'c{k}_counters'][:5])
+        assert np.all(np.abs(counters[k] - g[f'c{k}_counters']) <= edge)
+
+
 def test_melody_stats_softmax_layout_and_pipeline_evaluate(pl):
     """Column 0 = unvoiced logit (offset 1), through MelodyPipeline.evaluate on the shipped msnet parameters."""
     from oracle import post_oracle

@@ -166,3 +166,23 @@ def test_long_sequence_oracle_equals_the_single_threaded_one(oracle_c):
     A, pi = synth.dyadic_hmm(5, seed=1, coarse=True)
     E = synth.tie_stress((40, 5), 2)
     assert np.array_equal(c_oracle.viterbi_log_long_c(A, pi, E, nthreads=8)[0], c_oracle.viterbi_log_c(A, pi, E)[0])
+
+
+def test_post_oracle_equals_the_reference_statistics_step():
+    """oracle/post_oracle.py against goldens made by EXECUTING the reference's own viterbi_update_states_tf_fn + est_notes_fn
+    (dcnet/softmax_viterbi.py:1919-1958, 2923-2979) on a NumPy-backed stand-in for its TensorFlow ops
+    (tests/golden/make_golden.py melody_stats), and against the live reference where the checkout is present."""
+    from oracle import post_oracle as po
+    g = load('melody_stats.npz')
+    live = ref_loader.dcnet_melody_stats() if ref_loader.available() else None
+    for k in range(int(g['n_cases'])):
+        args = (g[f'c{k}_ref'], g[f'c{k}_logits'], g[f'c{k}_bins'], g[f'c{k}_voiced'])
+        est, c = po.melody_stats_np(*args)
+        assert np.allclose(est, g[f'c{k}_est'], rtol=1e-6, atol=1e-6)            # (np.exp may differ in the last ulp across machines)
+        got = np.asarray([c[n] for n in po.COUNTERS], np.int64)
+        diff = np.abs(np.abs(est) - args[0])
+        edge = int(np.sum(np.abs(diff - 0.5) < 2e-5) + np.sum(np.abs(np.abs(diff - np.round(diff / 12) * 12) - 0.5) < 2e-5))
+        assert np.all(np.abs(got - g[f'c{k}_counters']) <= edge) and np.array_equal(got[:5], g[f'c{k}_counters'][:5])
+        if live is not None:
+            est_l, c_l = live(*args)
+            assert np.array_equal(est_l, est) and list(c_l.values()) == [c[n] for n in po.COUNTERS]
