@@ -27,6 +27,8 @@
 namespace vit {
 
 constexpr int kEmisWarps = 8;
+// floats per shared-memory row of the generic kernel: reflect padding of spw either side, rounded up
+__host__ __device__ inline int emis_row_floats(int n_bins, int spw) { return (n_bins + 2 * spw + 8 + 3) & ~3; }
 constexpr float kTinyF = 1.1754943508222875e-38f;   // np.finfo(np.float32).tiny
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -61,23 +63,29 @@ __device__ __forceinline__ bool is_peak(const float* x, int n, int k, int spw) {
 //                    order as np.roll(ini_probs, 1) (dcnet/softmax_viterbi.py:2534-2538), or NULL for "unscaled".
 // model 1 (SHAUN)  : logits [B][T][n_bins]; threshold = logit(voicing threshold); p = 0.8, scale = 2 as in the reference.
 // out [B][T][n_bins + 1], unvoiced LAST (the np.roll(-1) at :2577; the shaun model writes it there directly).
-// SPW5: single_side_peak_width == 5 (dcnet / msnet / ftanet / tonet) takes the fast peak test: the frame is stored with
-// its reflect padding materialised, window maxima of width 2 and 4 are built by doubling, and
-//   left  max = max(m4[p-5], x[p-1]),  right max = max(m4[p+1], x[p+5])        (p = padded index of the bin)
-// -- 11 shared-memory accesses per bin instead of 21.  Any other width uses the direct neighbour scan.
-template <int MODEL, bool SPW5>
+// FAST (any single_side_peak_width >= 2: 5 dcnet / msnet / ftanet / tonet, 15 tonet/for_paper.py, 16 jdc, 20 imm): the
+// frame is stored with its reflect padding materialised and window maxima of width 2, 4, ... w2 (the largest power of two
+// <= spw) are built by doubling, ping-ponging between two rows; a window of width spw is then two overlapping windows of
+// width w2:
+//   left  max = max(m[k - spw], m[k - w2]),   right max = max(m[k + 1], m[k + 1 + spw - w2]),   m[j] = max(x[j .. j + w2 - 1])
+// -- 3 log2(w2) + 5 shared-memory accesses per bin instead of 2 spw + 1 (41 at spw = 20).  spw < 2: the direct scan.
+template <int MODEL, bool FAST, int kPre>
 __global__ void __launch_bounds__(32 * kEmisWarps)
 emissions_kernel(const float* __restrict__ logits, const float* __restrict__ prior, long long n_frames, int n_bins, int spw,
                  float threshold, int out_log, int pk_cap, float* __restrict__ out) {
-  // per warp: x, m2, m4 rows of n_bins + 16 floats, then the compacted peak list (bin, exp) of pk_cap entries -- peaks
-  // are more than spw bins apart, so pk_cap = n_bins / (spw + 1) + 2 suffices and 5 instead of 3 blocks fit an SM
+  // per warp: x and two window-maxima rows of np floats, then the compacted peak list (bin, exp) of pk_cap entries --
+  // peaks are more than spw bins apart, so pk_cap = n_bins / (spw + 1) + 2 suffices (5 instead of 3 blocks per SM at 360 bins)
   extern __shared__ float s_x[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int np = n_bins + 16;                                        // padded row: 5 + n_bins + 5, rounded up
+  const int pad = FAST ? spw : 0;
+  const int np = emis_row_floats(n_bins, spw);                       // padded row: spw + n_bins + spw, rounded up
   const int per_warp = 3 * np + 2 * pk_cap;
-  float* x = s_x + (size_t)w * per_warp + 5;                         // x[k] = logit of bin k; x[-5 .. n+4] valid
-  float* m2 = s_x + (size_t)w * per_warp + np + 5;
-  float* m4 = s_x + (size_t)w * per_warp + 2 * np + 5;
+  float* x = s_x + (size_t)w * per_warp + pad;                       // x[k] = logit of bin k; x[-spw .. n+spw-1] valid
+  float* ma = s_x + (size_t)w * per_warp + np + pad;
+  float* mb = s_x + (size_t)w * per_warp + 2 * np + pad;
+  int w2 = 1, levels = 0;                                            // largest power of two <= spw
+  while (2 * w2 <= spw) { w2 *= 2; ++levels; }
+  const float* m = (levels & 1) ? ma : mb;                           // the row that ends up holding the width-w2 maxima
   int* pk_idx = reinterpret_cast<int*>(s_x + (size_t)w * per_warp + 3 * np);   // compacted peak bins
   float* pk_e = s_x + (size_t)w * per_warp + 3 * np + pk_cap;        // exp(peak logit - max)
   const int n_in = MODEL == 0 ? n_bins + 1 : n_bins;
@@ -85,7 +93,7 @@ emissions_kernel(const float* __restrict__ logits, const float* __restrict__ pri
   const float zero_out = out_log ? logf(kTinyF) : 0.f;               // log(0 + tiny) = -87.33655
   // software pipeline over frames: the next frame's logits are fetched into registers (n_bins <= 384) before this frame
   // is processed, so the HBM latency hides under ~700 instructions of work instead of stalling every frame
-  constexpr int kPre = 12;
+  // (kPre = 12: up to 384 bins; 24: up to 768 -- jdc / imm have 721)
   const bool use_pre = n_bins <= 32 * kPre;
   const long long f_stride = (long long)gridDim.x * kEmisWarps;
   float pre[kPre];
@@ -118,16 +126,20 @@ emissions_kernel(const float* __restrict__ logits, const float* __restrict__ pri
       for (int k = lane; k < n_bins; k += 32) x[k] = vin[k];
       if (MODEL == 0) unv_now = in[0];
     }
-    if (SPW5) {
+    if (FAST) {
       __syncwarp();
-      if (lane < 5) {                                                // np.pad(mode='reflect'): -m -> m, n-1+m -> n-1-m
+      if (lane < spw) {                                              // np.pad(mode='reflect'): -m -> m, n-1+m -> n-1-m
         x[-1 - lane] = x[1 + lane];
         x[n_bins + lane] = x[n_bins - 2 - lane];
       }
       __syncwarp();
-      for (int k = lane - 5; k < n_bins + 4; k += 32) m2[k] = fmaxf(x[k], x[k + 1]);          // max of x[k .. k+1]
-      __syncwarp();
-      for (int k = lane - 5; k < n_bins + 2; k += 32) m4[k] = fmaxf(m2[k], m2[k + 2]);         // max of x[k .. k+3]
+      const float* src = x;
+      for (int l = 0, h = 1; l < levels; ++l, h *= 2) {              // dst[j] = max of x[j .. j + 2h - 1]
+        float* dst = (l & 1) ? mb : ma;
+        for (int k = lane - spw; k <= n_bins + spw - 2 * h; k += 32) dst[k] = fmaxf(src[k], src[k + h]);
+        __syncwarp();
+        src = dst;
+      }
     }
     __syncwarp();
     // pass 1: find the peaks and COMPACT them (ballot + prefix count) into a per-warp list, so that the expensive
@@ -136,9 +148,9 @@ emissions_kernel(const float* __restrict__ logits, const float* __restrict__ pri
     for (int k = lane; k < ((n_bins + 31) & ~31); k += 32) {
       bool pk = false;
       if (k < n_bins) {
-        if (SPW5) {
+        if (FAST) {
           const float c = x[k];
-          pk = (c > fmaxf(m4[k - 5], x[k - 1])) && (c >= fmaxf(m4[k + 1], x[k + 5]));
+          pk = (c > fmaxf(m[k - spw], m[k - w2])) && (c >= fmaxf(m[k + 1], m[k + 1 + spw - w2]));
         } else {
           pk = is_peak(x, n_bins, k, spw);
         }
@@ -412,6 +424,197 @@ emissions_reg_kernel(const float* __restrict__ logits, const float* __restrict__
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ---- wide register-window instance (single_side_peak_width 16 or 20, 24 < n_bins <= 756: jdc / imm, 721 bins) ----------
+// Same scheme as emissions_reg_kernel, for the fine-grid models (jdc/viterbi_softmax.py: 721 bins, half-width 16;
+// imm/main_imm.py:141-234: 721 bins, half-width 20): the frame's logits arrive by cp.async into a 3-deep ring of rows, two
+// frames ahead; a lane owns 12 consecutive bins in each of TWO passes over the row (bins [0, 384) and [384, 768)) and reads
+// them with their +-SPW neighbours as 11 / 13 conflict-free LDS.128 (lane stride 48 B).  The peak test stays in registers:
+// window maxima of width 3 and 9 by 3-input maxima (FMNMX3), then a window of 16 = two overlapping 9s, of 20 = three; peaks
+// are more than SPW >= 12 bins apart, so a lane finds at most ONE per pass -- the two value slots of the narrow kernel are
+// the two passes here, and lane 31's second slot (bins 756 ..: past n_bins) carries the unvoiced state.  Exact peaks; values
+// as in the other kernels (1e-5 relative to NumPy).
+constexpr int kWPer = 12;                            // bins per lane and pass
+constexpr int kWPass = 2;
+constexpr int kWBins = 32 * kWPer * kWPass;          // 768 bin slots
+constexpr int kWStages = 3;
+template <int SPW>
+struct WideEmis {
+  static_assert(SPW % 4 == 0 && SPW >= kWPer, "window alignment / one peak per pass");
+  static constexpr int XO = SPW + 4;                 // x[k] lives at row index k + XO; index 0 holds the unvoiced logit
+  static constexpr int ROW = (XO + kWBins + SPW + 7) & ~3;
+  static constexpr int NW = kWPer + 2 * SPW;         // window floats per lane and pass: 44 / 52
+  static constexpr int OUT = (3 + kWBins + 1 + 7) & ~3;
+  static constexpr int WARP_FLOATS = kWStages * ROW + OUT;
+};
+
+template <int MODEL, int SPW>
+__global__ void __launch_bounds__(32 * kEmisWarps, 2)
+emissions_wide_kernel(const float* __restrict__ logits, const float* __restrict__ prior, long long n_frames, int n_bins,
+                      float threshold, int out_log, float* __restrict__ out) {
+  using W = WideEmis<SPW>;
+  extern __shared__ __align__(16) float s_x[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* base = s_x + (size_t)w * W::WARP_FLOATS;
+  float* orow = base + kWStages * W::ROW;
+  const int n_in = MODEL == 0 ? n_bins + 1 : n_bins;
+  const int S = n_bins + 1;
+  const float zero_out = out_log ? logf(kTinyF) : 0.f;               // log(0 + tiny) = -87.33655
+  const long long f_stride = (long long)gridDim.x * kEmisWarps;
+  const long long f0 = (long long)blockIdx.x * kEmisWarps + w;
+  for (int i = lane; i < kWStages * W::ROW; i += 32) base[i] = 0.f;  // lanes past n_bins read these (results unused)
+  for (int i = lane; i < W::OUT; i += 32) orow[i] = zero_out;        // the output row: constant except at the peaks
+  __syncwarp();
+  const size_t in_step = (size_t)f_stride * n_in;
+  const float* in_fetch = logits + f0 * n_in + (MODEL == 0 ? 1 : 0) + lane;
+  long long f_fetch = f0;
+  auto fetch = [&](int st) {
+    if (f_fetch < n_frames) {
+      const uint32_t dst = smem_u32(base + st * W::ROW + W::XO + lane);
+#pragma unroll
+      for (int i = 0; i < kWBins / 32; ++i)
+        if (lane + 32 * i < n_bins) cp_async4(dst + 128 * i, in_fetch + 32 * i);
+      if (MODEL == 0 && lane == 0) cp_async4(dst - 4 * W::XO, in_fetch - 1);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    in_fetch += in_step;
+    f_fetch += f_stride;
+  };
+#pragma unroll
+  for (int s = 0; s < kWStages - 1; ++s) fetch(s);
+  int st = 0;
+  int a = (int)((f0 * S) & 3);                                       // alignment shift of the frame's output row
+  const int a_step = (int)((f_stride * S) & 3);
+  float* o_f = out + f0 * S;
+  const size_t out_step = (size_t)f_stride * S;
+  const bool unv_in_slot = n_bins <= kWBins - kWPer;                 // lane 31's pass-1 bins lie past n_bins
+  const float prior0 = (MODEL == 0 && prior) ? prior[0] : 1.f;
+  for (long long f = f0; f < n_frames; f += f_stride) {
+    {
+      int stn = st + kWStages - 1;
+      if (stn >= kWStages) stn -= kWStages;
+      fetch(stn);
+    }
+    asm volatile("cp.async.wait_group %0;" ::"n"(kWStages - 1) : "memory");
+    __syncwarp();
+    float* xr = base + st * W::ROW;
+    float* x = xr + W::XO;
+    if (lane < SPW) {                                                // np.pad(mode='reflect'): -m -> m, n-1+m -> n-1-m
+      x[-1 - lane] = x[1 + lane];
+      x[n_bins + lane] = x[n_bins - 2 - lane];
+    }
+    __syncwarp();
+    const float unv_logit = MODEL == 0 ? xr[0] : 0.f;                // column 0 is always a peak (:2521)
+    float cpk[kWPass];                                               // my peak's logit per pass (-inf: none)
+    int ipk[kWPass];                                                 // ... and its bin
+#pragma unroll
+    for (int p = 0; p < kWPass; ++p) {
+      const int kb = 32 * kWPer * p + kWPer * lane;                  // my first bin of this pass
+      // window: wv[j] = x[kb - SPW + j]; bin i of mine is wv[SPW + i]
+      float wv[W::NW];
+      {
+        const float4* w4 = reinterpret_cast<const float4*>(xr) + (kb + 4) / 4;
+#pragma unroll
+        for (int m = 0; m < W::NW / 4; ++m) {
+          const float4 v = w4[m];
+          wv[4 * m] = v.x; wv[4 * m + 1] = v.y; wv[4 * m + 2] = v.z; wv[4 * m + 3] = v.w;
+        }
+      }
+      float m3[W::NW - 2], m9[W::NW - 8];
+#pragma unroll
+      for (int j = 0; j < W::NW - 2; ++j) m3[j] = fmax3(wv[j], wv[j + 1], wv[j + 2]);
+#pragma unroll
+      for (int j = 0; j < W::NW - 8; ++j) m9[j] = fmax3(m3[j], m3[j + 3], m3[j + 6]);
+      float c_p = -INFINITY;
+      int i_p = -1;
+#pragma unroll
+      for (int i = 0; i < kWPer; ++i) {
+        const float c = wv[SPW + i];
+        // bin k is a peak iff x[k-SPW .. k-1] < x[k] and x[k+1 .. k+SPW] <= x[k]; a window of SPW starting at s:
+        const int sl = i, sr = SPW + i + 1;
+        float left, right;
+        if constexpr (SPW == 16) {
+          left = fmaxf(m9[sl], m9[sl + 7]);
+          right = fmaxf(m9[sr], m9[sr + 7]);
+        } else {
+          left = fmax3(m9[sl], m9[sl + 9], m9[sl + SPW - 9]);
+          right = fmax3(m9[sr], m9[sr + 9], m9[sr + SPW - 9]);
+        }
+        const bool pk = (kb + i < n_bins) && (c > left) && (c >= right);
+        c_p = pk ? c : c_p;
+        i_p = pk ? kb + i : i_p;
+      }
+      cpk[p] = c_p;
+      ipk[p] = i_p;
+    }
+    const bool v0 = ipk[0] >= 0, v1 = ipk[1] >= 0;
+    const int n_peaks = __reduce_add_sync(0xffffffffu, (v0 ? 1 : 0) + (v1 ? 1 : 0));
+    float mx = fmaxf(cpk[0], cpk[1]);
+    if (MODEL == 0) mx = fmaxf(mx, unv_logit);
+    mx = warp_max_redux_f32(mx);
+    const float e0 = v0 ? expf(cpk[0] - mx) : 0.f;
+    const float e1 = v1 ? expf(cpk[1] - mx) : 0.f;
+    float sum = warp_sum(e0 + e1);
+    float scale, p_unv;
+    if (MODEL == 0) {
+      const float eu = expf(unv_logit - mx);                         // softmax over the peaks and column 0 (:2565-2572)
+      sum += eu;
+      scale = __fdividef(1.f, sum);
+      p_unv = __fdividef(eu * scale, prior0);
+    } else {
+      if (n_peaks == 0) {
+        scale = 0.f;
+        p_unv = 1.f;                                                 // no peak: E[unvoiced] = 1 (imm/main_imm.py:203-205)
+      } else {
+        const float offset = logf(0.8f / (1.f - 0.8f));
+        const float sg = 2.f * (mx - threshold) + (mx >= threshold ? offset : -offset);   // (imm/main_imm.py:211-215)
+        float pv, qv;                                                // expit (:155-164)
+        if (sg > 0.f) { const float t = expf(-sg); pv = 1.f / (1.f + t); qv = t / (1.f + t); }
+        else { const float t = expf(sg); pv = t / (1.f + t); qv = 1.f / (1.f + t); }
+        scale = __fdividef(pv, sum);
+        p_unv = qv;
+      }
+    }
+    const bool s1_unv = unv_in_slot && lane == 31;
+    float p0v = e0 * scale, p1v = e1 * scale;
+    if (MODEL == 0 && prior) {                                       // then / priors (:2571-2572)
+      p0v = __fdividef(p0v, prior[v0 ? ipk[0] + 1 : 0]);
+      p1v = __fdividef(p1v, prior[v1 ? ipk[1] + 1 : 0]);
+    }
+    if (s1_unv) p1v = p_unv;
+    if (out_log) {
+      p0v = logf(p0v + kTinyF);
+      p1v = logf(p1v + kTinyF);
+    }
+    const int total = a + S;
+    const int k1 = a + (s1_unv ? n_bins : ipk[1]);
+    if (v0) orow[a + ipk[0]] = p0v;
+    if (v1 || s1_unv) orow[k1] = p1v;
+    if (!unv_in_slot && lane == 0) orow[a + n_bins] = out_log ? logf(p_unv + kTinyF) : p_unv;
+    __syncwarp();
+    {
+      float* oa = o_f - a;                                           // 16-byte aligned
+      const int j0 = a ? 1 : 0, j1 = total >> 2;
+#pragma unroll
+      for (int i = 0; i < (W::OUT / 4 + 31) / 32; ++i) {
+        const int j = lane + 32 * i;
+        if (j >= j0 && j < j1) reinterpret_cast<float4*>(oa)[j] = reinterpret_cast<const float4*>(orow)[j];
+      }
+      if (a && lane >= a && lane < 4) oa[lane] = orow[lane];         // head: the rest of the first float4
+      const int tl = 4 * j1 + lane;
+      if (lane < 4 && tl < total) oa[tl] = orow[tl];                 // tail
+    }
+    __syncwarp();                                                    // the row has been copied: constant back in place
+    if (v0) orow[a + ipk[0]] = zero_out;
+    if (v1 || s1_unv) orow[k1] = zero_out;
+    if (!unv_in_slot && lane == 0) orow[a + n_bins] = zero_out;
+    __syncwarp();
+    if (++st == kWStages) st = 0;
+    a = (a + a_step) & 3;
+    o_f += out_step;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // states -> (voiced, bins): voiced = s < n_bins; bins = min(s, n_bins - 1); frames past the clip's length (state -1)
 // give voiced = 0, bins = -1.
 __global__ void voiced_bins_kernel(const int64_t* __restrict__ states, long long n, int n_bins, uint8_t* __restrict__ voiced,
@@ -521,21 +724,44 @@ int emissions_run(const float* logits, const float* prior, int B, int T, int n_b
     VIT_CUDA_TRY(cudaGetLastError());
     return VIT_OK;
   }
-  const bool fast = spw == 5 && n_bins >= 7;
+  if ((spw == 16 || spw == 20) && n_bins > spw + 2 && n_bins <= kWBins - kWPer && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+      !no_reg) {
+    // the fine-grid models (jdc: 721 bins, half-width 16; imm: 20): wide register-window kernel, 2 blocks of 8 warps per SM
+    long long blocks = (n_frames + kEmisWarps - 1) / kEmisWarps;
+    const long long cap = (long long)num_sms * 2;
+    if (blocks > cap) blocks = cap;
+#define VIT_EMIS_WIDE(M, W_)                                                                                         \
+  do {                                                                                                              \
+    const size_t smem_w = (size_t)kEmisWarps * WideEmis<W_>::WARP_FLOATS * sizeof(float);                           \
+    VIT_CUDA_TRY(cudaFuncSetAttribute(emissions_wide_kernel<M, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w)); \
+    emissions_wide_kernel<M, W_><<<(unsigned)blocks, 32 * kEmisWarps, smem_w, stream>>>(logits, prior, n_frames, n_bins, \
+                                                                                         threshold, out_log, out); \
+  } while (0)
+    if (model == 0) { if (spw == 16) VIT_EMIS_WIDE(0, 16); else VIT_EMIS_WIDE(0, 20); }
+    else { if (spw == 16) VIT_EMIS_WIDE(1, 16); else VIT_EMIS_WIDE(1, 20); }
+#undef VIT_EMIS_WIDE
+    note_launch();
+    VIT_CUDA_TRY(cudaGetLastError());
+    return VIT_OK;
+  }
+  const bool fast = spw >= 2 && n_bins >= spw + 2;                   // (the reflect padding needs spw + 1 bins)
   const int pk_cap = (n_bins / (spw + 1) + 2 + 3) & ~3;              // peaks are more than spw bins apart
-  const size_t smem = (size_t)kEmisWarps * (3 * (n_bins + 16) + 2 * pk_cap) * sizeof(float);
+  const size_t smem = (size_t)kEmisWarps * (3 * emis_row_floats(n_bins, spw) + 2 * pk_cap) * sizeof(float);
+  if (smem > 200 * 1024) return VIT_ERR_UNSUPPORTED_ALGO;
   long long blocks = (n_frames + kEmisWarps - 1) / kEmisWarps;
   const long long cap = (long long)num_sms * 8;                      // grid-stride: a multiple of the SM count
   if (blocks > cap) blocks = cap;
-#define VIT_EMIS_LAUNCH(M, F)                                                                                       \
+#define VIT_EMIS_LAUNCH(M, F, P)                                                                                    \
   do {                                                                                                              \
     if (smem > 48 * 1024)                                                                                           \
-      VIT_CUDA_TRY(cudaFuncSetAttribute(emissions_kernel<M, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    emissions_kernel<M, F><<<(unsigned)blocks, 32 * kEmisWarps, smem, stream>>>(logits, prior, n_frames, n_bins, spw, \
-                                                                                threshold, out_log, pk_cap, out);  \
+      VIT_CUDA_TRY(cudaFuncSetAttribute(emissions_kernel<M, F, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    emissions_kernel<M, F, P><<<(unsigned)blocks, 32 * kEmisWarps, smem, stream>>>(logits, prior, n_frames, n_bins, spw, \
+                                                                                   threshold, out_log, pk_cap, out); \
   } while (0)
-  if (model == 0) { if (fast) VIT_EMIS_LAUNCH(0, true); else VIT_EMIS_LAUNCH(0, false); }
-  else { if (fast) VIT_EMIS_LAUNCH(1, true); else VIT_EMIS_LAUNCH(1, false); }
+#define VIT_EMIS_LAUNCH_P(M, F) do { if (n_bins <= 384) VIT_EMIS_LAUNCH(M, F, 12); else VIT_EMIS_LAUNCH(M, F, 24); } while (0)
+  if (model == 0) { if (fast) VIT_EMIS_LAUNCH_P(0, true); else VIT_EMIS_LAUNCH_P(0, false); }
+  else { if (fast) VIT_EMIS_LAUNCH_P(1, true); else VIT_EMIS_LAUNCH_P(1, false); }
+#undef VIT_EMIS_LAUNCH_P
 #undef VIT_EMIS_LAUNCH
   note_launch();
   VIT_CUDA_TRY(cudaGetLastError());
