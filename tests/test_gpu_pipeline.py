@@ -57,7 +57,8 @@ def test_shaun_model_matches_tonet_golden_and_full_pipeline(pl):
 
 
 @pytest.mark.parametrize('spw,n_bins', [(5, 64), (16, 100), (20, 721), (1, 3), (5, 7), (5, 13), (5, 360), (5, 383), (5, 384),
-                                        (5, 385), (5, 6)])
+                                        (5, 385), (5, 6), (16, 721), (16, 756), (20, 757), (16, 19), (20, 23), (15, 360),
+                                        (2, 9), (3, 50), (7, 700), (33, 400)])
 def test_peak_picking_is_exact_with_ties_and_reflect_padding(pl, spw, n_bins):
     """Quantised logits (many equal neighbours) against the NumPy argmax-of-window rule of
     find_peaks_all_at_once_np_fn (dcnet/softmax_viterbi.py:2508-2528), restated here for arbitrary width."""
@@ -103,6 +104,59 @@ def test_register_window_kernel_agrees_with_the_generic_kernel(pl, model, n_bins
         c2 = pl.emissions_device(logits, n_bins, m, prior, 5, 0.3, out_log=out_log, out=big[4:4 + a.numel()].view(a.shape))
         assert torch.equal(c2, a)
         assert bool(torch.isnan(big[:4]).all()) and bool(torch.isnan(big[-4:]).all())
+
+
+@pytest.mark.parametrize('model,n_bins,spw,scaled', [('softmax', 721, 16, True), ('shaun', 721, 20, False), ('softmax', 721, 20, False),
+                                                     ('shaun', 700, 16, False), ('softmax', 756, 16, True), ('shaun', 40, 20, False)])
+def test_wide_register_window_kernel_agrees_with_the_generic_kernel(pl, model, n_bins, spw, scaled, monkeypatch):
+    """Peak half-width 16 / 20 with up to 756 bins (jdc: 721 / 16, imm: 721 / 20) takes the wide register-window kernel (two
+    passes of 12 bins per lane, window maxima by 3-input maxima in registers); VIT_EMIS_GENERIC keeps the generic one.
+    Same peaks exactly, values within the softmax-sum rounding, nothing written outside the table."""
+    g = torch.Generator(device='cuda'); g.manual_seed(n_bins + spw)
+    n_in = n_bins + 1 if model == 'softmax' else n_bins
+    logits = 2 * torch.randn((3, 37, n_in), device='cuda', generator=g)
+    logits[0, 3] = 0.0                                                      # a flat frame: no voiced peak at all
+    logits[1, 5, n_in - 9:] = 9.0                                           # a plateau running into the reflected edge
+    logits[2, 7] = torch.round(logits[2, 7])                                # ties between neighbours
+    prior = (torch.rand((n_bins + 1,), device='cuda', generator=g) * 0.01 + 1e-3) if scaled else None
+    m = pl.SOFTMAX if model == 'softmax' else pl.SHAUN
+    for out_log in (True, False):
+        a = pl.emissions_device(logits, n_bins, m, prior, spw, 0.3, out_log=out_log)
+        monkeypatch.setenv('VIT_EMIS_GENERIC', '1')
+        b = pl.emissions_device(logits, n_bins, m, prior, spw, 0.3, out_log=out_log)
+        monkeypatch.delenv('VIT_EMIS_GENERIC')
+        zero = float(np.log(np.finfo(np.float32).tiny)) if out_log else 0.0
+        assert torch.equal(a == zero, b == zero)
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-4 if out_log else 0.0)
+        big = torch.full((a.numel() + 8,), float('nan'), dtype=torch.float32, device='cuda')
+        c2 = pl.emissions_device(logits, n_bins, m, prior, spw, 0.3, out_log=out_log, out=big[4:4 + a.numel()].view(a.shape))
+        assert torch.equal(c2, a)
+        assert bool(torch.isnan(big[:4]).all()) and bool(torch.isnan(big[-4:]).all())
+    # peaks against the NumPy window rule
+    x = logits[..., 1:] if model == 'softmax' else logits
+    x = x.cpu().numpy().reshape(-1, n_bins)
+    padded = np.pad(x, [(0, 0), (spw, spw)], mode='reflect')
+    want = np.lib.stride_tricks.sliding_window_view(padded, 2 * spw + 1, axis=1).argmax(-1) == spw
+    got = pl.emissions_device(logits, n_bins, m, prior, spw, 0.3, out_log=False).cpu().numpy().reshape(-1, n_bins + 1)
+    assert np.array_equal(got[:, :n_bins] != 0, want)
+
+
+@pytest.mark.parametrize('case_name', ['jdc_SoftMaxViterbi_True', 'jdc_Viterbi_0p5', 'imm_Viterbi'])
+def test_wide_kernel_against_goldens_made_by_the_reference_classes(pl, case_name):
+    """Emission tables of the jdc / imm models against the reference's own observation_probs_fn (tests/golden/class_calls.npz)."""
+    g = np.load(os.path.join(GOLD, 'class_calls.npz'))
+    logits, want = g[f'{case_name}_logits'], g[f'{case_name}_probs']
+    if case_name.startswith('jdc_SoftMax'):
+        prior = torch.as_tensor(np.roll(g['pi_jdc'], 1).astype(np.float32).copy()).cuda()
+        p = pl.emissions_device(torch.as_tensor(logits[None]).cuda(), 721, pl.SOFTMAX, prior, 16, 0.0, out_log=False)[0].cpu().numpy()
+        close(p, want)
+    elif case_name.startswith('jdc'):
+        p = pl.emissions_device(torch.as_tensor(logits[None]).cuda(), 721, pl.SHAUN, None, 16, 0.0, out_log=False)[0].cpu().numpy()
+        assert np.array_equal(p.T != 0, want != 0) and np.allclose(p.T, want, rtol=2e-5, atol=1e-7)
+    else:
+        x = np.ascontiguousarray(logits.T)                                     # imm hands logits over as [n_bins, T]
+        p = pl.emissions_device(torch.as_tensor(x[None]).cuda(), 721, pl.SHAUN, None, 20, 2.442347, out_log=False)[0].cpu().numpy()
+        assert np.array_equal(p.T != 0, want != 0) and np.allclose(p.T, want, rtol=2e-5, atol=1e-7)
 
 
 def test_voiced_bins_and_batched_pipeline(pl):
