@@ -12,27 +12,31 @@
 //                the canonical no-swizzle MN-major layout (8 x 16-byte core matrices; validated by
 //                tools/microbench_umma.cu), double buffered.  Each CTA writes the rows of its own states and pushes them
 //                to its peers with bulk-async DSMEM copies that complete on the receiver's mbarrier.
-//   * D        = fp32 in TMEM; 256 epilogue threads (two per row = state, CN / 2 clips each) read their row with
-//                tcgen05.ld, scale, multiply by the emission likelihoods, store alpha~ / gamma, and write the next V.
+//   * D        = fp32 in TMEM; the epilogue threads (two per row = state and sub-batch, 8 clips each) read their row
+//                with tcgen05.ld, scale, multiply by the emission likelihoods, store alpha~ / gamma, and write the next V.
 //
 // What round 2 changed (the round-1 kernel was ONE dependency chain per cluster -- wait V -> 48 MMAs -> epilogue ->
-// exchange, 5200 clocks per step, the tensor pipe idle 70 % of the time; profiles/r01k_*):
-//   * TWO independent sub-batches X and Y per cluster, each with its own accumulator and V buffers.  A dedicated MMA
-//     warp (warp 8) issues X's 48 MMAs, then Y's, then X's of the next step ...; the 8 epilogue warps work on Y's
-//     accumulator while X's MMAs run and vice versa, and a quadrant's rows are pushed to the peers by that quadrant's
-//     own warps the moment they are written -- so the exchange and the epilogue hide under the other sub-batch's MMAs
-//     and the step is bound by MMA issue (~27 clocks per N = 32 MMA, tools/microbench_umma_rate.cu,
-//     profiles/r02_microbench_umma_rate.jsonl).
+// exchange, 5200 clocks per step, the tensor pipe idle 70 % of the time; profiles/r01k_*): 19.2 -> 13.1 ms at 1024 x 3000 x 361
+//   * TWO independent sub-batches X and Y per cluster, each with its own accumulator, V buffers and 8 epilogue warps
+//     (warps 0-3, 8-11: X; 4-7, 12-15: Y).  A dedicated MMA warp (warp 16) issues X's 48 MMAs, then Y's, then X's of the
+//     next step ...; X's epilogue runs while Y's MMAs issue and vice versa; an exchange warp (warp 17) pushes a CTA's
+//     rows to its peers the moment its epilogue warps have written them.  MMA issue is ~27 clocks per N = 32 MMA
+//     (11 + N / 2: tools/microbench_umma_rate.cu, profiles/r02_microbench_umma_rate.jsonl), 2 x 1280 of the ~4600 clocks
+//     of a step pair; the rest is hand-off latency between the roles (DESIGN.md section 3.8 lists what was tried).
 //   * no block-wide barrier in the step: lane 31 of every TMEM quadrant holds no state; its operand row is all ones
 //     (forward), so D[that row] = sum_k alpha~[k] = the normaliser c_{t-1} arrives in every warp's own lane 31 and is
 //     broadcast with shuffles (round 1: one ones-row, a shared-memory broadcast and two __syncthreads per step).
 //   * the gamma renormalisation pass is gone (round 1: a separate HBM-bound kernel, read + write of gamma, 2 ms of 19).
 //     The bf16 products leave ~1e-5 of relative error per step in the SCALE of beta, common to all states of a frame,
-//     so gamma_t must be renormalised to sum 1.  Backward: every warp reduces gamma~_t of its 31 states x CN / 2 clips
+//     so gamma_t must be renormalised to sum 1.  Backward: every warp reduces gamma~_t of its 31 states x 8 clips
 //     with shuffles and parks the partial sums as "the V row of lane 31" (a spare K position); they travel to the peers
 //     with the rows anyway; the backward operand's lane-31 rows are indicators of those K positions, so the NEXT step's
 //     GEMM delivers s_t = sum_j gamma~_t[j] in every warp's lane 31 for free.  gamma~_t is held in registers for one
 //     step and stored as gamma~_t / s_t.
+//   * the step's inputs arrive by cp.async one step ahead; 1 / c is one MUFU.RCP (the IEEE division's range-check branch
+//     serialised ~110 clocks per quotient); the epilogue hands its V rows over BEFORE it stores to HBM.
+//   * -DVIT_FB_STAMPS prints clock stamps of one step of the MMA warp and of one epilogue warp (how all of the above was
+//     found).
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_bf16.h>
