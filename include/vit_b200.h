@@ -180,6 +180,29 @@ int vit_forward_backward_f32(const float* d_A, const float* d_pi, const float* d
                              int B, int T_max, int S, void* d_workspace, size_t workspace_bytes,
                              float* d_gamma, float* d_loglik, void* stream);
 
+/* Same, with an explicit kernel and the structure of the transition matrix.
+ *   VIT_FB_TC      tcgen05 tensor-core kernel (dense matrices, S <= 372; products as 2 x bf16 terms, fp32 accumulate)
+ *   VIT_FB_SIMT    dense FFMA kernel (any S the tensor-memory plan takes, e.g. 722)
+ *   VIT_FB_BANDED  band + one dense state, every other entry exactly 0 -- what viterbi_transition_matrix.py builds
+ *                  (dcnet/viterbi_transition_matrix.py:81-98): S (2d + 3) multiply-adds per frame instead of S^2, fp32.
+ *                  `structure` = vit_analyze_structure_f32 of the HOST copy of d_A (kind 1, background 0, halfwidth
+ *                  <= 14, S <= 384); VIT_ERR_UNSUPPORTED_ALGO otherwise.
+ *   VIT_FB_AUTO    banded when `structure` allows it, else tc, else simt (what vit_forward_backward_f32 does with
+ *                  structure = NULL).
+ * The workspace size does not depend on the kernel. */
+#define VIT_FB_AUTO 0
+#define VIT_FB_TC 1
+#define VIT_FB_SIMT 2
+#define VIT_FB_BANDED 3
+typedef struct vit_fb_opts {
+  int32_t impl;                       /* VIT_FB_* */
+  int32_t reserved;
+  const vit_structure* structure;     /* of d_A (probability domain); may be NULL */
+} vit_fb_opts;
+int vit_forward_backward_f32_ex(const float* d_A, const float* d_pi, const float* d_lik, const int32_t* d_lengths,
+                                int B, int T_max, int S, void* d_workspace, size_t workspace_bytes,
+                                float* d_gamma, float* d_loglik, const vit_fb_opts* opts, void* stream);
+
 /*
  * The step before the decode: acoustic-model logits -> HMM emission table, batched on the GPU.
  *   model VIT_EMIS_SOFTMAX (0): SoftMaxViterbi.observation_probs_fn, dcnet/softmax_viterbi.py:2508-2579:

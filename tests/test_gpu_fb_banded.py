@@ -1,0 +1,207 @@
+"""Banded forward-backward kernel (VIT_FB_BANDED behind vit_forward_backward_f32_ex, csrc/vit_fb_banded.cu) against the
+float64 oracle, and against the dense kernels on the same inputs.
+
+PARITY UNPINNED: the reference has no forward-backward code (oracle/fb_oracle.py defines the semantics).  The matrices
+are the ones the reference's builders produce (dcnet/viterbi_transition_matrix.py:81-98: a band of +-d_max bins inside a
+voiced/unvoiced switch, exact zeros elsewhere), which is the structure the kernel exploits.
+Tolerances are the north star's: 1e-4 absolute on gamma, 1e-5 relative on log L."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fb_oracle
+from viterbi_spl_b200 import hmm_params
+
+pytestmark = pytest.mark.gpu
+GAMMA_ATOL = 1e-4
+LOGLIK_RTOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def FB(cuda_lib):
+    assert torch.cuda.is_available()
+    os.environ.pop('VIT_FB_IMPL', None)
+    from viterbi_spl_b200 import ForwardBackward
+    return ForwardBackward
+
+
+def banded_hmm(S, d, dense, rng, zero_fraction=0.0):
+    """Row-stochastic [S, S]: band |i - j| <= d among the other states + one dense state (row and column), or no dense
+    state (dense = None).  zero_fraction knocks out entries inside the band as well."""
+    A = np.zeros((S, S))
+    i, j = np.indices((S, S))
+    band = np.abs(i - j) <= d
+    A[band] = rng.random(band.sum()) ** 2 + 1e-3
+    if zero_fraction:
+        A[band & (rng.random((S, S)) < zero_fraction) & (i != j)] = 0
+    if dense is not None:
+        A[dense, :] = rng.random(S) * 0.01 + 1e-4
+        A[:, dense] = rng.random(S) * 0.05 + 1e-3
+    A /= A.sum(1, keepdims=True)
+    pi = rng.random(S) + 0.01
+    return A.astype(np.float32), (pi / pi.sum()).astype(np.float32)
+
+
+def peaky_likelihoods(B, T, S, rng):
+    """0-5 peaks per frame + the last state, other bins exactly 0 (SoftMaxViterbi.observation_probs_fn shape,
+    dcnet/softmax_viterbi.py:2530-2579)."""
+    lik = np.zeros((B, T, S), np.float32)
+    for b in range(B):
+        for t in range(T):
+            k = int(rng.integers(0, 6))
+            idx = np.unique(np.append(rng.choice(S - 1, size=min(k, S - 1), replace=False), S - 1))
+            w = np.exp(2.0 * rng.standard_normal(len(idx)))
+            lik[b, t, idx] = w / w.sum()
+    return lik
+
+
+def check(FB, A, pi, lik, lengths=None, impl='banded'):
+    want_g, want_ll = fb_oracle.forward_backward_batch_np(A, pi, lik, lengths)
+    fb = FB(A, pi, impl=impl)
+    assert fb.structured
+    g, ll = fb.run_host(lik, lengths)
+    assert g.dtype == np.float32 and g.shape == lik.shape
+    assert not np.isnan(g).any()
+    err = np.abs(g - want_g).max()
+    assert err <= GAMMA_ATOL, f'max |gamma error| {err}'
+    assert np.allclose(ll, want_ll, rtol=LOGLIK_RTOL, atol=1e-5), (ll, want_ll)
+    if lengths is None:
+        assert np.allclose(g.sum(-1), 1, atol=1e-4)
+    else:
+        for b, n in enumerate(lengths):
+            assert np.all(g[b, n:] == 0)
+    return g, ll
+
+
+@pytest.mark.parametrize('S,d,dense,T,B', [
+    (3, 1, None, 3, 1), (5, 1, 4, 7, 3), (16, 2, 0, 9, 4), (33, 4, 32, 40, 9), (64, 3, None, 20, 8), (97, 5, 40, 50, 5),
+    (127, 8, 126, 30, 7), (128, 7, 0, 12, 16), (200, 12, 199, 64, 9), (255, 11, 100, 10, 3), (321, 12, 320, 60, 17),
+    (361, 14, 360, 80, 30), (383, 14, 382, 10, 3), (384, 13, None, 10, 5), (384, 14, 383, 6, 11)])
+def test_random_banded_models(FB, S, d, dense, T, B):
+    rng = np.random.default_rng(S * 31 + d)
+    A, pi = banded_hmm(S, d, dense, rng, zero_fraction=0.2 if S > 60 else 0.0)
+    lik = np.exp(2 * rng.standard_normal((B, T, S))).astype(np.float32)
+    check(FB, A, pi, lik)
+
+
+@pytest.mark.parametrize('state_set', ['dcnet', 'tonet'])
+def test_reference_state_sets_ragged(FB, state_set):
+    A, pi = hmm_params.synthetic_hmm(state_set)
+    S = len(pi)
+    rng = np.random.default_rng(S)
+    B, T = 20, 120
+    lik = peaky_likelihoods(B, T, S, rng)
+    L = rng.integers(0, T + 1, size=B).astype(np.int32)
+    L[:5] = [T, 1, 0, 2, T]
+    check(FB, A.astype(np.float32), pi.astype(np.float32), lik, L)
+
+
+def test_auto_takes_the_banded_kernel_and_agrees_with_the_dense_ones(FB, cuda_lib):
+    from viterbi_spl_b200 import _lib
+    A, pi = hmm_params.synthetic_hmm('tonet')
+    A, pi = A.astype(np.float32), pi.astype(np.float32)
+    rng = np.random.default_rng(1)
+    lik = np.exp(rng.standard_normal((9, 50, 361))).astype(np.float32)
+    n0 = _lib.launch_count()
+    g_auto, ll_auto = FB(A, pi).run_host(lik)
+    assert _lib.launch_count() - n0 == 3                  # two banded passes + log L (the dense kernels pack first: 5)
+    g_b, ll_b = FB(A, pi, impl='banded').run_host(lik)
+    assert np.array_equal(g_auto, g_b) and np.array_equal(ll_auto, ll_b)
+    for impl in ('tc', 'simt'):
+        g_d, ll_d = FB(A, pi, impl=impl).run_host(lik)
+        assert np.abs(g_d - g_b).max() <= GAMMA_ATOL
+        assert np.allclose(ll_d, ll_b, rtol=LOGLIK_RTOL)
+
+
+def test_dense_matrix_is_refused_by_the_banded_kernel_and_auto_falls_back(FB):
+    from viterbi_spl_b200._lib import VitError
+    rng = np.random.default_rng(0)
+    A = rng.random((50, 50)).astype(np.float32)
+    A /= A.sum(1, keepdims=True)
+    pi = np.full(50, 0.02, np.float32)
+    lik = (rng.random((3, 8, 50)) + 0.1).astype(np.float32)
+    fb = FB(A, pi, impl='banded')
+    assert not fb.structured
+    with pytest.raises(VitError):
+        fb.run_host(lik)
+    want_g, _ = fb_oracle.forward_backward_batch_np(A, pi, lik)
+    g, _ = FB(A, pi).run_host(lik)
+    assert np.abs(g - want_g).max() <= GAMMA_ATOL
+
+
+def test_more_clips_than_one_pass_of_the_grid(FB):
+    """1500 ragged clips at S = 361: more than the 148 x 8 co-resident ones, so the CTAs loop."""
+    A, pi = hmm_params.synthetic_hmm('tonet')
+    rng = np.random.default_rng(11)
+    B, T, S = 1500, 10, 361
+    lik = np.exp(rng.standard_normal((B, T, S))).astype(np.float32)
+    L = rng.integers(0, T + 1, size=B).astype(np.int32)
+    L[::7] = T
+    check(FB, A.astype(np.float32), pi.astype(np.float32), lik, L)
+
+
+def test_long_clip_does_not_underflow(FB):
+    A, pi = hmm_params.synthetic_hmm('tonet')
+    rng = np.random.default_rng(3)
+    lik = peaky_likelihoods(2, 3000, 361, rng) * np.float32(1e-3)
+    check(FB, A.astype(np.float32), pi.astype(np.float32), lik)
+
+
+def test_impossible_observation_sequence_gives_zero_gamma_not_nan(FB):
+    S, T = 40, 16
+    rng = np.random.default_rng(5)
+    A = np.zeros((S, S), np.float32)
+    for d in (-1, 0, 1):
+        i = np.arange(max(0, -d), min(S, S - d))
+        A[i, i + d] = 1.0
+    A /= A.sum(1, keepdims=True)
+    pi = np.full(S, 1.0 / S, np.float32)
+    lik = (rng.random((3, T, S)) + 0.1).astype(np.float32)
+    lik[1, 6] = 0
+    lik[1, 6, 0] = 1.0
+    lik[1, 7] = 0
+    lik[1, 7, 30] = 1.0
+    fb = FB(A, pi, impl='banded')
+    g, ll = fb.run_host(lik)
+    assert not np.isnan(g).any()
+    assert np.all(g[1] == 0) and ll[1] == -np.inf
+    want_g, want_ll = fb_oracle.forward_backward_batch_np(A, pi, lik[[0, 2]])
+    assert np.abs(g[[0, 2]] - want_g).max() <= GAMMA_ATOL and np.allclose(ll[[0, 2]], want_ll, rtol=LOGLIK_RTOL)
+
+
+def test_c_abi_directly(cuda_lib):
+    """vit_forward_backward_f32_ex through ctypes with an explicit vit_fb_opts; inputs are not modified."""
+    from viterbi_spl_b200 import _lib
+    rng = np.random.default_rng(2)
+    A, pi = banded_hmm(100, 6, 99, rng)
+    st = _lib.analyze_structure(A)
+    assert st.kind == 1 and st.halfwidth == 6 and st.dense_index == 99 and st.background == 0.0
+    B, T, S = 5, 33, 100
+    lik = torch.rand((B, T, S), device='cuda') + 0.05
+    keep = lik.clone()
+    dA, dpi = torch.as_tensor(A).cuda(), torch.as_tensor(pi).cuda()
+    n = ctypes.c_size_t(0)
+    assert cuda_lib.vit_fb_workspace_bytes(B, T, S, ctypes.byref(n)) == 0
+    ws = torch.empty(n.value, dtype=torch.uint8, device='cuda')
+    gamma = torch.full((B, T, S), float('nan'), device='cuda')
+    ll = torch.empty(B, device='cuda')
+    opts = _lib.FbOpts()
+    opts.impl = _lib.FB_BANDED
+    opts.structure = ctypes.pointer(st)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = cuda_lib.vit_forward_backward_f32_ex(p(dA), p(dpi), p(lik), None, B, T, S, p(ws), n.value, p(gamma), p(ll),
+                                               ctypes.byref(opts), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(lik, keep)
+    want_g, want_ll = fb_oracle.forward_backward_batch_np(A, pi, lik.cpu().numpy())
+    assert np.abs(gamma.cpu().numpy() - want_g).max() <= GAMMA_ATOL
+    assert np.allclose(ll.cpu().numpy(), want_ll, rtol=LOGLIK_RTOL)
+    # a structure with a non-zero background is refused
+    st2 = _lib.Structure(1, 6, 99, -87.0, 0.0)
+    opts.structure = ctypes.pointer(st2)
+    assert cuda_lib.vit_forward_backward_f32_ex(p(dA), p(dpi), p(lik), None, B, T, S, p(ws), n.value, p(gamma), p(ll),
+                                                ctypes.byref(opts), None) == -4

@@ -76,9 +76,12 @@ def test_cfg3_722_states_10000_frames_8_clips_against_the_oracle(Decoder, model,
     torch.cuda.empty_cache()
 
 
-def test_cfg4_forward_backward_1024x3000x361_8_clips_against_the_float64_oracle(cuda_lib):
+@pytest.mark.parametrize('impl', ['tc', 'banded'])
+def test_cfg4_forward_backward_1024x3000x361_8_clips_against_the_float64_oracle(cuda_lib, impl):
+    """Config 4 at its named size with the tcgen05 kernel (what the config names) and with the banded kernel (what
+    `auto` takes for this matrix: band +-14 + the unvoiced state, exact zeros elsewhere)."""
     from viterbi_spl_b200 import ForwardBackward
-    os.environ.pop('VIT_FB_IMPL', None)                             # the default: tcgen05 where the shape fits
+    os.environ.pop('VIT_FB_IMPL', None)
     B, T, S = 1024, 3000, 361
     A, pi = hmm_params.synthetic_hmm('tonet')
     A, pi = A.astype(np.float32), pi.astype(np.float32)
@@ -100,7 +103,9 @@ def test_cfg4_forward_backward_1024x3000x361_8_clips_against_the_float64_oracle(
             np.put_along_axis(host[k], idx, (w[:, :4] / pi[idx]).astype(np.float32), axis=1)
             host[k][:, S - 1] = (w[:, 4] / pi[S - 1]).astype(np.float32)
     lik[torch.as_tensor(where, device=dev)] = torch.as_tensor(host).to(dev)
-    gamma, ll = ForwardBackward(A, pi).run_device(lik)
+    fb = ForwardBackward(A, pi, impl=impl)
+    assert fb.structured
+    gamma, ll = fb.run_device(lik)
     got_g, got_l = gamma[where].cpu().numpy(), ll[where].cpu().numpy()
     want_g, want_l = fb_oracle.forward_backward_batch_np(A, pi, host)
     assert np.abs(got_g - want_g).max() <= 1e-4

@@ -14,6 +14,7 @@ ap.add_argument('--frames', type=int, default=3000)
 ap.add_argument('--states', type=int, default=361)
 ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--warmup', type=int, default=2)
+ap.add_argument('--impl', default='auto')
 a = ap.parse_args()
 B, T, S = a.clips, a.frames, a.states
 A, pi = hmm_params.synthetic_hmm({321: 'dcnet', 361: 'tonet', 722: 'jdc'}[S])
@@ -21,7 +22,7 @@ A, pi = A.astype(np.float32), pi.astype(np.float32)
 dev = torch.device('cuda')
 g = torch.Generator(device=dev); g.manual_seed(4)
 lik = torch.softmax(2.0 * torch.randn((B, T, S), device=dev, generator=g), dim=-1)       # dense softmax likelihoods
-fb = ForwardBackward(A, pi)
+fb = ForwardBackward(A, pi, impl=a.impl)
 gamma = torch.empty_like(lik); ll = torch.empty(B, device=dev)
 for _ in range(a.warmup):
     fb.run_device(lik, None, gamma, ll)
@@ -48,7 +49,7 @@ wg, wl = fb_oracle.forward_backward_batch_np(A, pi, lik[sub].cpu().numpy())
 err = float(np.abs(gamma[sub].cpu().numpy() - wg).max())
 rel = float(np.abs((ll[sub].cpu().numpy() - wl) / wl).max())
 print(json.dumps({'metric': 'forward_backward_frames_per_sec', 'value': B * T / (ms * 1e-3), 'unit': 'frames/s',
-                  'ms_per_step': ms, 'config': {'workload': f'scaled forward-backward {B} x {T} x {S}', 'dtype': 'f32'},
+                  'ms_per_step': ms, 'config': {'workload': f'scaled forward-backward {B} x {T} x {S}', 'dtype': 'f32', 'impl': a.impl},
                   'roofline_tensor': {'bound': 'tensor', 'achieved': mma_flops / (ms * 1e-3) / 1e12, 'peak': tensor_peak,
                                       'unit': 'TFLOP/s (bf16 MMA flops executed)', 'frac': mma_flops / (ms * 1e-3) / 1e12 / tensor_peak,
                                       'note': 'tcgen05 kernel only (S <= 372); the FFMA kernel executes no MMA'},

@@ -17,7 +17,7 @@ ALGO_NAMES = {'auto': ALGO_AUTO, 'backpointer': ALGO_BACKPOINTER, 'cluster': ALG
 # every symbol include/vit_b200.h declares (tests/test_abi.py checks the built library exports them all)
 EXPORTS = ['vit_version', 'vit_strerror', 'vit_last_cuda_error', 'vit_launch_count', 'vit_select_algo',
            'vit_workspace_bytes', 'vit_decode_f32', 'vit_decode_f32_ex', 'vit_upload_frames_f32',
-           'vit_fb_workspace_bytes', 'vit_forward_backward_f32', 'vit_emissions_f32', 'vit_voiced_bins',
+           'vit_fb_workspace_bytes', 'vit_forward_backward_f32', 'vit_forward_backward_f32_ex', 'vit_emissions_f32', 'vit_voiced_bins',
            'vit_analyze_structure_f32', 'vit_clips_in_flight', 'vit_melody_stats_f32']
 
 
@@ -35,6 +35,15 @@ class DecodeOpts(ctypes.Structure):
                 ('frame_begin', ctypes.c_int32), ('frame_end', ctypes.c_int32),
                 ('skip_backtrace', ctypes.c_int32), ('reserved2', ctypes.c_int32),
                 ('structure', ctypes.POINTER(Structure)), ('backtrace_stream', ctypes.c_void_p)]
+
+
+class FbOpts(ctypes.Structure):
+    """struct vit_fb_opts"""
+    _fields_ = [('impl', ctypes.c_int32), ('reserved', ctypes.c_int32), ('structure', ctypes.POINTER(Structure))]
+
+
+FB_AUTO, FB_TC, FB_SIMT, FB_BANDED = 0, 1, 2, 3
+FB_IMPLS = {'auto': FB_AUTO, 'tc': FB_TC, 'simt': FB_SIMT, 'banded': FB_BANDED}
 
 
 class VitError(RuntimeError):
@@ -73,6 +82,8 @@ def load():
     L.vit_fb_workspace_bytes.argtypes = [ci, ci, ci, ctypes.POINTER(sz)]
     L.vit_forward_backward_f32.restype = ci
     L.vit_forward_backward_f32.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp, vp, vp]
+    L.vit_forward_backward_f32_ex.restype = ci
+    L.vit_forward_backward_f32_ex.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp, sz, vp, vp, ctypes.POINTER(FbOpts), vp]
     L.vit_analyze_structure_f32.restype = ci
     L.vit_analyze_structure_f32.argtypes = [vp, ci, ctypes.POINTER(Structure)]
     L.vit_clips_in_flight.restype = ci

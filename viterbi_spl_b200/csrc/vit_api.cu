@@ -89,15 +89,29 @@ bool fb_tc_supported(int S);
 size_t fb_tc_workspace_bytes(int B, int T_max, int S);
 int fb_tc_run(const float* A, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S,
               void* workspace, size_t workspace_bytes, float* gamma, float* loglik, cudaStream_t stream);
-// Which of the two forward-backward kernels runs: the tcgen05 tensor-core kernel wherever the shape fits (S <= 381: the
-// bf16 hi/lo image of a 127-row shard plus the accumulators must fit the 512 TMEM columns) -- measured 19.2 ms vs the
-// FFMA kernel's 46.2 ms at 1024 x 3000 x 361 -- else the FFMA kernel (S = 722).
-// VIT_FB_IMPL=tc|simt forces one of them where the shape allows (tests run both).
-static bool fb_use_tc(int B, int S) {
-  (void)B;
-  const char* e = getenv("VIT_FB_IMPL");
-  if (e && !strcmp(e, "simt") && fb_supported(S)) return false;
-  return fb_tc_supported(S);
+// vit_fb_banded.cu
+bool fb_banded_supported(int S, const vit_structure* st);
+size_t fb_banded_workspace_bytes(int B, int T_max);
+int fb_banded_run(const float* A, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S,
+                  const vit_structure* st, void* workspace, size_t workspace_bytes, float* gamma, float* loglik,
+                  cudaStream_t stream);
+// Which forward-backward kernel runs (VIT_FB_AUTO): the banded FFMA kernel when the caller passed the structure of a
+// band + dense-state matrix (S (2d+3) instead of S^2 multiply-adds per frame; every matrix the reference's builders
+// produce); else the tcgen05 tensor-core kernel wherever the shape fits (S <= 372: the bf16 hi/lo image of a 124-row
+// shard plus the accumulators must fit the 512 TMEM columns) -- 13.1 ms vs the FFMA kernel's 46.2 ms at
+// 1024 x 3000 x 361 -- else the dense FFMA kernel (S = 722).
+// VIT_FB_IMPL=tc|simt|banded forces one of them where the shape allows (tests run all three).
+static int fb_pick_impl(int S, const vit_fb_opts* opts) {
+  int impl = opts ? opts->impl : VIT_FB_AUTO;
+  const vit_structure* st = opts ? opts->structure : nullptr;
+  if (impl == VIT_FB_AUTO) {
+    const char* e = getenv("VIT_FB_IMPL");
+    if (e && !strcmp(e, "simt") && fb_supported(S)) return VIT_FB_SIMT;
+    if (e && !strcmp(e, "tc") && fb_tc_supported(S)) return VIT_FB_TC;
+    if (fb_banded_supported(S, st)) return VIT_FB_BANDED;
+    return fb_tc_supported(S) ? VIT_FB_TC : VIT_FB_SIMT;
+  }
+  return impl;
 }
 
 static int check_shape(int B, int T_max, int S) {
@@ -279,21 +293,34 @@ int vit_fb_workspace_bytes(int B, int T_max, int S, size_t* out_bytes) {
   return VIT_OK;
 }
 
-int vit_forward_backward_f32(const float* d_A, const float* d_pi, const float* d_lik, const int32_t* d_lengths, int B,
-                             int T_max, int S, void* d_workspace, size_t workspace_bytes, float* d_gamma,
-                             float* d_loglik, void* stream) {
+int vit_forward_backward_f32_ex(const float* d_A, const float* d_pi, const float* d_lik, const int32_t* d_lengths, int B,
+                                int T_max, int S, void* d_workspace, size_t workspace_bytes, float* d_gamma,
+                                float* d_loglik, const vit_fb_opts* opts, void* stream) {
   int rc = check_shape(B, T_max, S);
   if (rc != VIT_OK) return rc;
   if (!d_A || !d_pi || !d_gamma || (!d_lik && B > 0)) return VIT_ERR_INVALID_ARGUMENT;
   if (!fb_supported(S) && !fb_tc_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;
   if (!d_workspace) return VIT_ERR_WORKSPACE_TOO_SMALL;
   if (((uintptr_t)d_workspace & 255u) != 0) return VIT_ERR_MISALIGNED;
-  if (fb_use_tc(B, S))
+  const int impl = fb_pick_impl(S, opts);
+  if (impl == VIT_FB_BANDED)
+    return fb_banded_run(d_A, d_pi, d_lik, d_lengths, B, T_max, S, opts ? opts->structure : nullptr, d_workspace,
+                         workspace_bytes, d_gamma, d_loglik, (cudaStream_t)stream);
+  if (impl == VIT_FB_TC) {
+    if (!fb_tc_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;
     return fb_tc_run(d_A, d_pi, d_lik, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_gamma, d_loglik,
                      (cudaStream_t)stream);
-  if (!fb_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;
+  }
+  if (impl != VIT_FB_SIMT || !fb_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;
   return fb_run(d_A, d_pi, d_lik, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_gamma, d_loglik, nullptr,
                 nullptr, (cudaStream_t)stream);
+}
+
+int vit_forward_backward_f32(const float* d_A, const float* d_pi, const float* d_lik, const int32_t* d_lengths, int B,
+                             int T_max, int S, void* d_workspace, size_t workspace_bytes, float* d_gamma,
+                             float* d_loglik, void* stream) {
+  return vit_forward_backward_f32_ex(d_A, d_pi, d_lik, d_lengths, B, T_max, S, d_workspace, workspace_bytes, d_gamma,
+                                     d_loglik, nullptr, stream);
 }
 
 int vit_emissions_f32(const float* d_logits, const float* d_prior, int B, int T, int n_bins, int model,

@@ -23,7 +23,10 @@ def _ptr(t):
 class ForwardBackward:
     """gamma_t[j] = P(state_t = j | all frames) and log L for batches of clips; float32 on the GPU."""
 
-    def __init__(self, transition_matrix, init_probs, device=None):
+    def __init__(self, transition_matrix, init_probs, device=None, impl='auto'):
+        """impl: 'auto' (the banded kernel when the matrix is band + one dense state with exact zeros elsewhere -- every
+        matrix the reference's builders produce -- else the tcgen05 kernel, else the dense FFMA kernel), or 'banded' /
+        'tc' / 'simt' to force one (VitError if the shape or the matrix does not allow it)."""
         if not torch.cuda.is_available():
             raise RuntimeError('viterbi_spl_b200 needs a CUDA device (B200); there is no CPU fallback')
         self.lib = _lib.load()
@@ -38,6 +41,18 @@ class ForwardBackward:
         self.A = A.to(self.device).contiguous()
         self.pi = pi.to(self.device).contiguous()
         self._ws = None
+        # band + dense-state structure of the (probability-domain) matrix, found once on the host
+        self.structure = _lib.analyze_structure(A.detach().cpu().numpy())
+        self.impl = _lib.FB_IMPLS[impl]
+        self._opts = _lib.FbOpts()
+        self._opts.impl = self.impl
+        self._opts.structure = ctypes.pointer(self.structure)
+
+    @property
+    def structured(self):
+        """True when 'auto' takes the banded kernel for this matrix (unless VIT_FB_IMPL overrides it)."""
+        st = self.structure
+        return bool(st.kind == 1 and st.background == 0.0 and st.halfwidth <= 14 and 2 <= self.S <= 384)
 
     def run_device(self, lik, lengths=None, gamma=None, loglik=None):
         """lik: CUDA float32 [B, T, S] likelihoods (>= 0); lengths: CUDA int32 [B] or None.
@@ -58,9 +73,9 @@ class ForwardBackward:
             if loglik is None:
                 loglik = torch.empty((B,), dtype=torch.float32, device=self.device)
             st = torch.cuda.current_stream()
-            _lib.check(self.lib.vit_forward_backward_f32(_ptr(self.A), _ptr(self.pi), _ptr(lik), _ptr(lengths), B, T, S,
-                                                         _ptr(self._ws), self._ws.numel(), _ptr(gamma), _ptr(loglik),
-                                                         ctypes.c_void_p(st.cuda_stream)))
+            _lib.check(self.lib.vit_forward_backward_f32_ex(_ptr(self.A), _ptr(self.pi), _ptr(lik), _ptr(lengths), B, T, S,
+                                                            _ptr(self._ws), self._ws.numel(), _ptr(gamma), _ptr(loglik),
+                                                            ctypes.byref(self._opts), ctypes.c_void_p(st.cuda_stream)))
         return gamma, loglik
 
     def run_host(self, lik, lengths=None):
