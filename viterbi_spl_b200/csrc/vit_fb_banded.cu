@@ -55,7 +55,10 @@ __device__ __forceinline__ void fpipe_bar_sync(int cs) {
 __device__ __forceinline__ float frcp_pos(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  if (x < 1.1754944e-38f) r = x > 0.f ? 1.f / x : 0.f;
+  if (x < 1.1754944e-38f) {                               // zero or denormal: rescale by 2^64 either side (no division call)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 18446744073709551616.f));
+    r = x > 0.f ? r * 18446744073709551616.f : 0.f;
+  }
   return r;
 }
 // Sums over the 32 lanes of a warp of NV values per lane by recursive halving; value k ends up in the lanes whose top
@@ -169,7 +172,6 @@ fb_banded_pass_kernel(const float* __restrict__ A, const float* __restrict__ pi,
   const float a_dd = jd >= 0 ? A[(size_t)jd * S + jd] : 0.f;
   const bool wfull = __all_sync(0xffffffffu, jn_ok[0] && jn_ok[1] && jn_ok[2] && jn_ok[3]);
   const long long gamma_delta = reinterpret_cast<const char*>(gamma) - reinterpret_cast<const char*>(lik);
-  const int jd_off = jd - j0;
   // Global loads and stores are NOT done in the owner layout (lane l <-> states 4 l .. 4 l + 3: a warp-wide 4-byte access
   // at a 16-byte lane stride spans 512 bytes = 4-5 LSU wavefronts and 4-way bank conflicts on the shared-memory side);
   // lane l moves elements 128 tgw + l + 32 n of its warp's 128-state chunk instead (one wavefront per instruction), and
@@ -194,16 +196,19 @@ fb_banded_pass_kernel(const float* __restrict__ A, const float* __restrict__ pi,
 #pragma unroll
     for (int c = 0; c < CPT; ++c) maxlen = max(maxlen, len[c]);
     if (maxlen == 0) return;
-    // running pointer to lik[clip][t][j0]; the gamma buffer sits at a fixed distance.  A slot past the batch aliases the
+    // running pointer to element jc0 of the lik row staged LAST (one step ahead of the step being computed); the row
+    // this step writes (gamma buffer) sits at the fixed byte distance odelta from it.  A slot past the batch aliases the
     // last clip's rows (its length is 0: nothing is stored), a clip shorter than its pipeline's longest keeps stepping.
-    const float* pe[CPT];
+    const float* pin[CPT];
     int cni[CPT];                                           // cnorm index of frame 0 of my clips
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
       const int b = min(seq0 + c0 + c, B - 1);
-      pe[c] = lik + ((size_t)b * T_max + (BWD ? maxlen - 1 : 0)) * S + j0;
+      pin[c] = lik + ((size_t)b * T_max + (BWD ? maxlen - 1 : 0)) * S + jc0;
       cni[c] = b * T_max;
     }
+    const long long dS = BWD ? -(long long)S : (long long)S;
+    const long long odelta = gamma_delta - dS * 4;
     float xd[CPT];                                          // the dense state's value of the previous step
 #pragma unroll
     for (int c = 0; c < CPT; ++c) xd[c] = 0.f;
@@ -211,22 +216,20 @@ fb_banded_pass_kernel(const float* __restrict__ A, const float* __restrict__ pi,
 #pragma unroll
     for (int c = 0; c < CPT; ++c) cnext[c] = 1.f;
 
-    // requests the inputs of step it_f (frame t_f) into stage buffer it_f & 1; `rows` = how many steps the running
-    // pointers pe[] are behind that frame (0 or 1)
-    auto stage = [&](int it_f, int rows) {
+    // requests the inputs of step it_f (frame t_f; pin[] points at its rows) into stage buffer it_f & 1
+    auto stage = [&](int it_f) {
       if (it_f < maxlen) {
         const int t_f = BWD ? maxlen - 1 - it_f : it_f;
         const int b2 = it_f & 1;
-        const long long row_off = (long long)rows * (BWD ? -S : S);
         const bool pf = (lane & 7) == 0 && (BWD ? t_f >= 4 : t_f + 4 < T_max);
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
-          const float* src = pe[c] + row_off - j0 + jc0;    // element jc0 of the row
+          const float* src = pin[c];
           const float* srca = reinterpret_cast<const float*>(reinterpret_cast<const char*>(src) + gamma_delta);
           if (pf) {
             // a step is shorter than an HBM round trip: pull the lines 4 frames further into L2 now
             // (lanes 0, 8, 16, 24: one per 128-byte line of the warp's 512-byte chunk)
-            const long long far = 4ll * (BWD ? -S : S) - lane + (lane >> 3) * 32;
+            const long long far = 4 * dS - lane + (lane >> 3) * 32;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(src + far));
             if (BWD) asm volatile("prefetch.global.L2 [%0];" ::"l"(srca + far));
           }
@@ -248,7 +251,7 @@ fb_banded_pass_kernel(const float* __restrict__ A, const float* __restrict__ pi,
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    stage(0, 0);
+    stage(0);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     fpipe_bar_sync(cs);
 
@@ -258,11 +261,14 @@ fb_banded_pass_kernel(const float* __restrict__ A, const float* __restrict__ pi,
       const int t = BWD ? maxlen - 1 - it : it;
       const int buf = it & 1;
       const bool fin = !BWD && it == maxlen;               // forward tail: no frame to load
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) asm volatile("" : "+l"(pe[c]));
       // this step's inputs are in stage buffer `buf` (complete and visible since the barrier that ended the previous
       // step); the next step's are requested now
-      stage(it + 1, 1);
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        pin[c] += dS;
+        asm volatile("" : "+l"(pin[c]));     // (keep the running pointers in registers: ptxas re-derives them otherwise)
+      }
+      stage(it + 1);
       float v[CPT][fNJ], xdn[CPT];
       if (!BWD && it == 0) {
         // alpha~_0 = pi * b_0
@@ -326,7 +332,7 @@ fb_banded_pass_kernel(const float* __restrict__ A, const float* __restrict__ pi,
             const float4 e4 = reinterpret_cast<const float4*>(s_in[cs][buf][0][c])[tg];
             const float4 al4 = reinterpret_cast<const float4*>(s_in[cs][buf][KINDS - 1][c])[tg];
             const float e[fNJ] = {e4.x, e4.y, e4.z, e4.w}, al[fNJ] = {al4.x, al4.y, al4.z, al4.w};
-            float* pg = reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<float*>(pe[c])) + gamma_delta);
+            float* po = reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<float*>(pin[c])) + odelta);
             float g[fNJ];
 #pragma unroll
             for (int n = 0; n < fNJ; ++n) {
@@ -338,13 +344,12 @@ fb_banded_pass_kernel(const float* __restrict__ A, const float* __restrict__ pi,
             reinterpret_cast<float4*>(s_g[cs][c])[tg] = make_float4(g[0], g[1], g[2], g[3]);
             __syncwarp();
             if (lv) {
-              float* po = pg - j0 + jc0;
 #pragma unroll
               for (int n = 0; n < fNJ; ++n)
                 if (cfull || cp_ok[n]) st_global_cs_f32(po + 32 * n, s_g[cs][c][jc0 + 32 * n]);
             }
             const float bed = last ? 1.f : dd * invn;
-            if (jd >= 0 && tgw == 0 && lane == 1 && lv) st_global_cs_f32(pg + jd_off, (s_ind[cs][buf][1][c] * invc) * bed);
+            if (jd >= 0 && tgw == 0 && lane == 1 && lv) st_global_cs_f32(po + (jd - jc0), (s_ind[cs][buf][1][c] * invc) * bed);
             xdn[c] = (lv && jd >= 0) ? s_ind[cs][buf][0][c] * bed : 0.f;
             cnext[c] = ct;
           }
@@ -368,7 +373,7 @@ fb_banded_pass_kernel(const float* __restrict__ A, const float* __restrict__ pi,
           // alpha~_t -> the gamma buffer, read back from the row just written in the lane-contiguous layout
           __syncwarp();
           if (!fin && t < len[c]) {
-            float* po = reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<float*>(pe[c])) + gamma_delta) - j0 + jc0;
+            float* po = reinterpret_cast<float*>(reinterpret_cast<char*>(const_cast<float*>(pin[c])) + odelta);
 #pragma unroll
             for (int n = 0; n < fNJ; ++n)
               if (cfull || cp_ok[n]) st_global_cs_f32(po + 32 * n, s_v[cs][buf][c][DP + jc0 + 32 * n]);
@@ -376,7 +381,6 @@ fb_banded_pass_kernel(const float* __restrict__ A, const float* __restrict__ pi,
           }
         }
         xd[c] = xdn[c];
-        pe[c] += BWD ? -S : S;
       }
       if constexpr (BWD) {
         // only the dense state's row is summed over the warp
