@@ -107,13 +107,90 @@ def test_auto_takes_the_banded_kernel_and_agrees_with_the_dense_ones(FB, cuda_li
     lik = np.exp(rng.standard_normal((9, 50, 361))).astype(np.float32)
     n0 = _lib.launch_count()
     g_auto, ll_auto = FB(A, pi).run_host(lik)
-    assert _lib.launch_count() - n0 == 3                  # two banded passes + log L (the dense kernels pack first: 5)
+    # form check + two convolution passes + two general banded passes (which return at once here) + log L
+    assert _lib.launch_count() - n0 == 6
     g_b, ll_b = FB(A, pi, impl='banded').run_host(lik)
     assert np.array_equal(g_auto, g_b) and np.array_equal(ll_auto, ll_b)
     for impl in ('tc', 'simt'):
         g_d, ll_d = FB(A, pi, impl=impl).run_host(lik)
         assert np.abs(g_d - g_b).max() <= GAMMA_ATOL
         assert np.allclose(ll_d, ll_b, rtol=LOGLIK_RTOL)
+
+
+def toeplitz_hmm(n_bins, d, dense, rng, floor=2):
+    """The reference's recipe (dcnet/viterbi_transition_matrix.py:60-98): one jump histogram on every row of the band,
+    rows normalised, embedded in a voiced/unvoiced switch; dense = 'last' | 'first' | None."""
+    hist = np.maximum(np.floor(2e5 * np.exp(-np.abs(np.arange(-d, d + 1)) / 1.3) * (1 + 0.1 * rng.random(2 * d + 1))), floor)
+    hist = hist / hist.sum()
+    T = np.zeros((n_bins, n_bins), np.float32)
+    for i in range(n_bins):
+        for j in range(max(0, i - d), min(n_bins, i + d + 1)):
+            T[i, j] = hist[j - i + d]
+    T = T / np.sum(T, axis=1)[:, None]
+    if dense is None:
+        A = T
+    else:
+        sw = np.asarray([[0.9779, 0.0221], [0.0172, 0.9828]], np.float32)
+        A = np.zeros((n_bins + 1, n_bins + 1), np.float32)
+        v = slice(0, n_bins) if dense == 'last' else slice(1, n_bins + 1)
+        u = n_bins if dense == 'last' else 0
+        A[v, v] = T * sw[0, 0]
+        A[v, u] = sw[0, 1]
+        A[u, v] = sw[1, 0] / n_bins
+        A[u, u] = sw[1, 1]
+    S = A.shape[0]
+    pi = rng.random(S) + 0.01
+    return A.astype(np.float32), (pi / pi.sum()).astype(np.float32)
+
+
+def run_both_forms(FB, A, pi, lik, lengths=None):
+    """The same call with the convolution kernels allowed (default) and switched off (VIT_FB_CONV=0: general banded
+    kernels); both against the oracle.  Returns whether the two runs differ in any bit (= different kernels ran)."""
+    g1, l1 = check(FB, A, pi, lik, lengths)
+    os.environ['VIT_FB_CONV'] = '0'
+    try:
+        g0, l0 = check(FB, A, pi, lik, lengths)
+    finally:
+        os.environ.pop('VIT_FB_CONV', None)
+    assert np.abs(g1 - g0).max() <= 2e-5
+    return not np.array_equal(g1, g0)
+
+
+@pytest.mark.parametrize('n_bins,d,dense,T,B', [
+    (360, 14, 'last', 90, 21), (320, 12, 'last', 70, 9), (360, 13, 'last', 33, 5), (383, 14, 'last', 20, 4),
+    (384, 14, None, 20, 4), (200, 8, 'first', 40, 7), (120, 4, 'last', 50, 6), (61, 3, None, 25, 3), (40, 14, 'last', 30, 5)])
+def test_scaled_toeplitz_matrices_take_the_convolution_kernels(FB, n_bins, d, dense, T, B):
+    rng = np.random.default_rng(n_bins + d)
+    A, pi = toeplitz_hmm(n_bins, d, dense, rng)
+    S = len(pi)
+    lik = peaky_likelihoods(B, T, S, rng) if d % 2 else np.exp(2 * rng.standard_normal((B, T, S))).astype(np.float32)
+    L = rng.integers(0, T + 1, size=B).astype(np.int32)
+    L[:3] = [T, 1, 0][:min(3, B)]
+    assert run_both_forms(FB, A, pi, lik, L)
+
+
+def test_general_band_does_not_take_the_convolution_kernels(FB):
+    rng = np.random.default_rng(9)
+    A, pi = banded_hmm(200, 9, 199, rng)
+    lik = np.exp(rng.standard_normal((5, 40, 200))).astype(np.float32)
+    assert not run_both_forms(FB, A, pi, lik)
+
+
+def test_convolution_form_long_clips_1024_clip_batch(FB):
+    """More clips than are co-resident (148 SMs x 15 one-warp blocks), 400 frames, the tonet state set."""
+    A, pi = hmm_params.synthetic_hmm('tonet')
+    A, pi = A.astype(np.float32), pi.astype(np.float32)
+    dev = torch.device('cuda')
+    B, T, S = 2500, 400, 361
+    g = torch.Generator(device=dev)
+    g.manual_seed(6)
+    lik = torch.softmax(2.0 * torch.randn((B, T, S), device=dev, generator=g), dim=-1)
+    gamma, ll = FB(A, pi).run_device(lik)
+    assert torch.allclose(gamma.sum(-1), torch.ones((B, T), device=dev), atol=1e-4)
+    sub = [0, 1, 1234, 2499]
+    want_g, want_ll = fb_oracle.forward_backward_batch_np(A, pi, lik[sub].cpu().numpy())
+    assert np.abs(gamma[sub].cpu().numpy() - want_g).max() <= GAMMA_ATOL
+    assert np.allclose(ll[sub].cpu().numpy(), want_ll, rtol=LOGLIK_RTOL)
 
 
 def test_dense_matrix_is_refused_by_the_banded_kernel_and_auto_falls_back(FB):

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libvit_b200.so')
-SOURCES = ['vit_api.cu', 'vit_backpointer.cu', 'vit_cluster.cu', 'vit_tmem.cu', 'vit_fb.cu', 'vit_emis.cu', 'vit_banded.cu', 'vit_banded_wide.cu', 'vit_fb_tc.cu', 'vit_stream.cu', 'vit_fb_banded.cu']
+SOURCES = ['vit_api.cu', 'vit_backpointer.cu', 'vit_cluster.cu', 'vit_tmem.cu', 'vit_fb.cu', 'vit_emis.cu', 'vit_banded.cu', 'vit_banded_wide.cu', 'vit_fb_tc.cu', 'vit_stream.cu', 'vit_fb_banded.cu', 'vit_fb_conv.cu']
 HEADERS = ['vit_common.cuh', 'vit_tmem.cuh', os.path.join('..', '..', 'include', 'vit_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '--compiler-options', '-fPIC', '-shared', '-Xptxas', '-v']
@@ -30,6 +30,7 @@ KERNEL_SOURCES = {
     'fb_tc_pass_kernel': ['vit_fb_tc.cu', 'vit_common.cuh'],
     'fb_pass_kernel': ['vit_fb.cu', 'vit_tmem.cuh', 'vit_common.cuh'],
     'fb_banded_pass_kernel': ['vit_fb_banded.cu', 'vit_tmem.cuh', 'vit_common.cuh'],
+    'fb_conv_pass_kernel': ['vit_fb_conv.cu', 'vit_common.cuh'],
     'emissions_reg_kernel': ['vit_emis.cu', 'vit_common.cuh'],
 }
 

@@ -91,7 +91,9 @@ template <int D, bool BWD>
 __global__ void __launch_bounds__(fThreads, 1)
 fb_banded_pass_kernel(const float* __restrict__ A, const float* __restrict__ pi, const float* __restrict__ lik,
                       const int32_t* __restrict__ lengths, int B, int T_max, int S, int jd, float* __restrict__ gamma,
-                      float* __restrict__ cnorm, int q) {
+                      float* __restrict__ cnorm, int q, const int* __restrict__ conv_flag) {
+  // the matrix has the scaled-Toeplitz form and the convolution kernels (vit_fb_conv.cu) have done the work
+  if (*conv_flag != 0) return;
   constexpr int W = 2 * D + 1;
   constexpr int DP = (D + 3) / 4 * 4;
   constexpr int U0 = DP - D;                         // window element of cell (r, n) = w[U0 + r + n]
@@ -446,7 +448,14 @@ bool fb_banded_supported(int S, const vit_structure* st) {
   return fb_banded_template_D(st->halfwidth) > 0;
 }
 
-size_t fb_banded_workspace_bytes(int B, int T_max) { return align_up((size_t)(B > 0 ? B : 1) * T_max * sizeof(float), 256); }
+// vit_fb_conv.cu: the scaled-Toeplitz form (what the reference's builders produce) as a convolution, one warp per clip
+size_t fb_conv_params_bytes();
+int fb_conv_detect(const float* A, int S, const vit_structure* st, int Dt, void* params, cudaStream_t stream);
+int fb_conv_passes(int D, const void* params, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max,
+                   int S, int jd, float* gamma, float* cnorm, cudaStream_t stream);
+
+static size_t fb_banded_cnorm_bytes(int B, int T_max) { return align_up((size_t)(B > 0 ? B : 1) * T_max * sizeof(float), 256); }
+size_t fb_banded_workspace_bytes(int B, int T_max) { return fb_banded_cnorm_bytes(B, T_max) + fb_conv_params_bytes(); }
 
 int fb_banded_run(const float* A, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S,
                   const vit_structure* st, void* workspace, size_t workspace_bytes, float* gamma, float* loglik,
@@ -456,9 +465,16 @@ int fb_banded_run(const float* A, const float* pi, const float* lik, const int32
   if (workspace_bytes < fb_banded_workspace_bytes(B, T_max)) return VIT_ERR_WORKSPACE_TOO_SMALL;
   if (B == 0) return VIT_OK;
   float* cnorm = (float*)workspace;
+  void* conv_params = (char*)workspace + fb_banded_cnorm_bytes(B, T_max);     // its first word is the verdict
   // frames past a clip's length carry gamma = 0
   if (lengths) VIT_CUDA_TRY(cudaMemsetAsync(gamma, 0, (size_t)B * T_max * S * sizeof(float), stream));
   const int D = fb_banded_template_D(st->halfwidth);
+  // Scaled-Toeplitz check on the device, then BOTH kernel pairs: the convolution kernels return at once unless the
+  // check passed, the general kernels return at once if it did -- no round trip to the host.
+  int rc = fb_conv_detect(A, S, st, D, conv_params, stream);
+  if (rc != VIT_OK) return rc;
+  rc = fb_conv_passes(D, conv_params, pi, lik, lengths, B, T_max, S, st->dense_index, gamma, cnorm, stream);
+  if (rc != VIT_OK) return rc;
   int num_sms = 148, dev = 0;
   VIT_CUDA_TRY(cudaGetDevice(&dev));
   VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -477,8 +493,10 @@ int fb_banded_run(const float* A, const float* pi, const float* lik, const int32
     auto kb = fb_banded_pass_kernel<DD, true>;                                                                        \
     VIT_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));                 \
     VIT_CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));                 \
-    kf<<<grid, fThreads, smem_f, stream>>>(A, pi, lik, lengths, B, T_max, S, st->dense_index, gamma, cnorm, q);       \
-    kb<<<grid, fThreads, smem_b, stream>>>(A, pi, lik, lengths, B, T_max, S, st->dense_index, gamma, cnorm, q);       \
+    kf<<<grid, fThreads, smem_f, stream>>>(A, pi, lik, lengths, B, T_max, S, st->dense_index, gamma, cnorm, q,        \
+                                           (const int*)conv_params);                                                  \
+    kb<<<grid, fThreads, smem_b, stream>>>(A, pi, lik, lengths, B, T_max, S, st->dense_index, gamma, cnorm, q,        \
+                                           (const int*)conv_params);                                                  \
   } break;
   switch (D) {
     VIT_FBB_CASE(4) VIT_FBB_CASE(8) VIT_FBB_CASE(12) VIT_FBB_CASE(14)

@@ -1,0 +1,340 @@
+// Forward-backward for SCALED-TOEPLITZ bands: the form the reference's transition matrices actually have.
+//
+// dcnet/viterbi_transition_matrix.py:81-98 (and the tonet / jdc / imm copies) fill the band with ONE jump histogram,
+// `transition_matrix[i, j] = d_trans[j - i + d_max]`, normalise every row, and embed the result in the voiced/unvoiced
+// switch with constant entries to and from the unvoiced state.  So, apart from rounding,
+//
+//     A[i][j] = kappa_i * b[j - i]   (|j - i| <= d),      A[i][u] = r,      A[u][j] = q,      A[u][u] = a_uu
+//
+// with ONE tap vector b (2d + 1 values) and a per-source scale kappa_i (1 for interior rows, > 1 for the truncated rows
+// near the ends).  The band product is then a CONVOLUTION:  (alpha A)[j] = sum_i (alpha_i kappa_i) b[j - i]  (forward),
+// (A w)[i] = kappa_i sum_j b[j - i] w[j]  (backward).  A thread needs 2d + 1 tap registers whatever the number of states it
+// owns -- against 4 x (2d + 1) band registers for 4 states in the general kernel (vit_fb_banded.cu) -- so ONE WARP takes a
+// whole clip (12 consecutive states per lane, 384 >= S) and the step needs no block barrier, no per-warp partial sums in
+// shared memory and a third fewer instructions per state; the dense state's row and column are scalars
+// (sum_band alpha * r, alpha_u * q).  Clips are independent warps: 16 per SM hide each other's latencies.
+//
+// fb_conv_detect_kernel checks the form ON THE DEVICE at every call (the API only has the device copy of A): kappa_i =
+// sum of row i's band / sum of the taps it covers, every band entry within 2e-6 relative of kappa_i b[j - i] (measured on
+// the reference recipes: 2.3e-7 .. 5.7e-7, i.e. the rounding of the row normalisation), constant dense row / column,
+// kappa_i > 0.  The verdict is a flag in the workspace; the convolution kernels return at once when it is 0 and the
+// general banded kernels when it is 1, so nothing synchronises with the host.  Replacing A by kappa_i b[j - i] perturbs
+// every entry by a few ulps -- the same order as the kernel's own fp32 rounding; |gamma - float64 oracle| (which uses
+// the TRUE matrix) is checked at 1e-4 like every other kernel (tests/test_gpu_fb_banded.py).  Parity unpinned: the
+// reference has no forward-backward (oracle/fb_oracle.py).
+#include <cstdlib>
+
+#include "vit_common.cuh"
+
+namespace vit {
+
+constexpr int vNJ = 12;                    // consecutive states per lane
+constexpr int vMaxS = 32 * vNJ;            // 384
+constexpr int vDP = 16;                    // state i lives at float index i + vDP of a vector row
+constexpr int vRow = vMaxS + 2 * vDP;      // 416
+constexpr int vStages = 3;                 // input rows are fetched two steps ahead
+constexpr int vMaxTaps = 32;
+
+struct ConvParams {
+  int flag;                                // 1: the matrix has the scaled-Toeplitz form, the convolution kernels run
+  float r_in;                              // A[i][u]: every band state -> the dense state
+  float q_out;                             // A[u][j]: the dense state -> every band state
+  float a_uu;
+  float tap[vMaxTaps];                     // tap[x + Dt] = b[x], x = j - i, Dt = the kernel instance's half-width
+  float kappa[vMaxS];
+};
+
+size_t fb_conv_params_bytes() { return align_up(sizeof(ConvParams), 256); }
+
+// one block of 384 threads; thread i checks source row i
+__global__ void fb_conv_detect_kernel(const float* __restrict__ A, int S, int jd, int d, int Dt, int enable,
+                                      ConvParams* __restrict__ prm) {
+  // d: the band's half-width; Dt >= d: the half-width of the kernel instance that will run (taps are stored for it)
+  __shared__ float s_b[vMaxTaps];
+  __shared__ int s_istar;
+  __shared__ float s_rq[2];
+  const int i = threadIdx.x, W = 2 * d + 1;
+  if (i == 0) {
+    // a source row whose whole band exists: the taps are read from it
+    int istar = -1;
+    for (int k = 0; k < S && istar < 0; ++k) {
+      const int c = (S / 2 + k) % S;
+      if (c - d >= 0 && c + d < S && (jd < c - d || jd > c + d)) istar = c;
+    }
+    s_istar = (enable && S <= vMaxS && 2 * Dt + 1 <= vMaxTaps && d <= Dt) ? istar : -1;
+    // the constants every dense-row / dense-column entry must equal
+    const int i0 = jd == 0 ? 1 : 0;
+    s_rq[0] = (jd >= 0 && S > 1) ? A[(size_t)i0 * S + jd] : 0.f;
+    s_rq[1] = (jd >= 0 && S > 1) ? A[(size_t)jd * S + i0] : 0.f;
+  }
+  __syncthreads();
+  const int istar = s_istar;
+  if (istar < 0) {
+    if (i == 0) prm->flag = 0;
+    return;
+  }
+  if (i == 0) {
+    float sum = 0.f;
+    for (int r = 0; r < W; ++r) sum += A[(size_t)istar * S + istar + r - d];
+    for (int r = 0; r < W; ++r) s_b[r] = sum > 0.f ? A[(size_t)istar * S + istar + r - d] / sum : 0.f;
+  }
+  __syncthreads();
+  bool ok = true;
+  float kap = 0.f;
+  if (i < S && i != jd) {
+    float sa = 0.f, sb = 0.f;
+    for (int r = 0; r < W; ++r) {
+      const int j = i + r - d;
+      if (j >= 0 && j < S && j != jd) { sa += A[(size_t)i * S + j]; sb += s_b[r]; }
+    }
+    kap = sb > 0.f ? sa / sb : 0.f;
+    ok = kap > 0.f && kap < 1e30f;
+    for (int r = 0; r < W; ++r) {
+      const int j = i + r - d;
+      if (j >= 0 && j < S && j != jd) {
+        const float ref = kap * s_b[r];
+        ok = ok && fabsf(A[(size_t)i * S + j] - ref) <= 2e-6f * ref + 1e-37f;
+      }
+    }
+    if (jd >= 0) {
+      ok = ok && fabsf(A[(size_t)i * S + jd] - s_rq[0]) <= 2e-6f * s_rq[0];
+      ok = ok && fabsf(A[(size_t)jd * S + i] - s_rq[1]) <= 2e-6f * s_rq[1];
+    }
+  }
+  const int all_ok = __syncthreads_and(ok ? 1 : 0);
+  if (i < vMaxS) prm->kappa[i] = (i < S && i != jd) ? kap : 0.f;
+  if (i < vMaxTaps) {
+    const int x = i - Dt;                                  // tap[x + Dt] = b[x]
+    prm->tap[i] = (x >= -d && x <= d) ? s_b[x + d] : 0.f;
+  }
+  if (i == 0) {
+    prm->flag = all_ok;
+    prm->r_in = s_rq[0];
+    prm->q_out = s_rq[1];
+    prm->a_uu = jd >= 0 ? A[(size_t)jd * S + jd] : 0.f;
+  }
+}
+
+__device__ __forceinline__ float vrcp_pos(float x) {        // as frcp_pos in vit_fb_banded.cu
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  if (x < 1.1754944e-38f) {
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 18446744073709551616.f));
+    r = x > 0.f ? r * 18446744073709551616.f : 0.f;
+  }
+  return r;
+}
+__device__ __forceinline__ float vwarp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// One warp (= one block) per clip.
+template <int D, bool BWD>
+__global__ void __launch_bounds__(32, 16)
+fb_conv_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict__ pi, const float* __restrict__ lik,
+                    const int32_t* __restrict__ lengths, int T_max, int S, int jd, float* __restrict__ gamma,
+                    float* __restrict__ cnorm) {
+  if (prm->flag == 0) return;
+  constexpr int W = 2 * D + 1;
+  constexpr int U0 = vDP - D;                         // row offset (relative to 12 lane) of the first window element
+  constexpr int M0 = U0 / 4, M1 = (U0 + vNJ - 1 + 2 * D) / 4;    // float4s of a lane's window: [M0, M1]
+  constexpr int KINDS = BWD ? 2 : 1;
+  extern __shared__ __align__(16) float sm[];
+  float* s_row = sm;                                  // [2][vRow]: the vector the sweep reads (forward: alpha~ kappa, backward: w)
+  float* s_in = sm + 2 * vRow;                        // [vStages][KINDS][vMaxS]: b_t (and alpha~_t) rows, fetched by cp.async
+  float* s_out = s_in + vStages * KINDS * vMaxS;      // [vMaxS]: this step's output row on its way to HBM
+
+  const int lane = threadIdx.x;
+  const int b = blockIdx.x;
+  const int len = lengths ? lengths[b] : T_max;
+  if (len <= 0) return;
+  const int j0 = vNJ * lane;
+
+  float tap[W], kap[vNJ];
+#pragma unroll
+  for (int r = 0; r < W; ++r) tap[r] = prm->tap[BWD ? W - 1 - r : r];      // tap[(out - in) + D]
+#pragma unroll
+  for (int n = 0; n < vNJ; ++n) kap[n] = prm->kappa[j0 + n];               // 0 for the dense state and states >= S
+  const float r_in = prm->r_in, q_out = prm->q_out, a_uu = prm->a_uu;
+  const bool has_d = jd >= 0;
+
+  for (int x = lane; x < 2 * vRow; x += 32) s_row[x] = 0.f;
+  for (int x = lane; x < vStages * KINDS * vMaxS; x += 32) s_in[x] = 0.f;
+  __syncwarp();
+
+  // lane-contiguous element ownership for everything that touches HBM: lane l moves elements l + 32 n of a row
+  bool cp_ok[vNJ];
+#pragma unroll
+  for (int n = 0; n < vNJ; ++n) cp_ok[n] = lane + 32 * n < S && lane + 32 * n != jd;
+  const long long dS = BWD ? -(long long)S : (long long)S;
+  const long long gamma_delta = reinterpret_cast<const char*>(gamma) - reinterpret_cast<const char*>(lik);
+  const float* pin = lik + ((size_t)b * T_max + (BWD ? len - 1 : 0)) * S + lane;     // row staged next
+  float* pout = gamma + ((size_t)b * T_max + (BWD ? len - 1 : 0)) * S + lane;        // row written next
+  float* pc = cnorm + (size_t)b * T_max;
+
+  // requests the input rows of step it_f into stage buffer it_f % vStages (the dense state's slot is copied like any
+  // other and read as a scalar; it never enters the vector row the sweep reads)
+  auto stage = [&](int it_f) {
+    if (it_f < len) {
+      float* dst = s_in + (it_f % vStages) * KINDS * vMaxS + lane;
+      const uint32_t d0 = smem_u32(dst), d1 = smem_u32(dst + (KINDS - 1) * vMaxS);
+      const float* srca = reinterpret_cast<const float*>(reinterpret_cast<const char*>(pin) + gamma_delta);
+#pragma unroll
+      for (int n = 0; n < vNJ; ++n)
+        if (lane + 32 * n < S) {                         // (the dense state's slot is copied too: read as a scalar below)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 128 * n), "l"(pin + 32 * n) : "memory");
+          if (BWD) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d1 + 128 * n), "l"(srca + 32 * n) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    pin += dS;
+  };
+  stage(0);
+  stage(1);
+
+  float xd = 0.f;          // the dense state's value of the previous step (forward: alpha~_{t-1}[u]; backward: w_{t+1}[u])
+  float sband = 0.f;       // sum over the band states of the previous step's vector
+  float cprev = 1.f;       // backward: c_{t+1}
+  float cnext = BWD ? pc[len - 1] : 0.f;                   // backward: c_t of the coming step, loaded one step ahead
+  const int n_steps = len;
+  for (int it = 0; it < n_steps; ++it) {
+    const int t = BWD ? len - 1 - it : it;
+    const int buf = it & 1;
+    stage(it + 2);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncwarp();
+    const float* in = s_in + (it % vStages) * KINDS * vMaxS;
+    // my 12 states' inputs (the dense state's slot and the slots past S count for nothing: kappa = 0, masks below)
+    float e[vNJ];
+#pragma unroll
+    for (int m = 0; m < vNJ / 4; ++m) {
+      const float4 x = reinterpret_cast<const float4*>(in)[3 * lane + m];
+      e[4 * m] = x.x; e[4 * m + 1] = x.y; e[4 * m + 2] = x.z; e[4 * m + 3] = x.w;
+    }
+    const float ed = has_d ? in[jd] : 0.f;
+    float v[vNJ], xdn, out_d;                              // the new vector, its dense element, the dense element's output
+    float o[vNJ];                                          // what goes to HBM
+    if (!BWD && it == 0) {
+      // alpha~_0 = pi * b_0
+#pragma unroll
+      for (int n = 0; n < vNJ; ++n) v[n] = kap[n] > 0.f ? pi[j0 + n] * e[n] : 0.f;
+      xdn = has_d ? pi[jd] * ed : 0.f;
+#pragma unroll
+      for (int n = 0; n < vNJ; ++n) o[n] = v[n];
+      out_d = xdn;
+    } else {
+      // the band: acc[out] = sum_in row[in] tap[(out - in) + D]
+      float acc[vNJ];
+#pragma unroll
+      for (int n = 0; n < vNJ; ++n) acc[n] = 0.f;
+      const float4* row4 = reinterpret_cast<const float4*>(s_row + (buf ^ 1) * vRow) + 3 * lane;
+#pragma unroll
+      for (int m = M0; m <= M1; ++m) {
+        const float4 x = row4[m];
+        const float wv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int n = 0; n < vNJ; ++n) {
+            const int rr = n - (4 * m + k) + vDP + D;      // in = 12 lane + 4 m + k - vDP, out = 12 lane + n
+            if (rr >= 0 && rr < W) acc[n] = fmaf(wv[k], tap[rr], acc[n]);
+          }
+      }
+      if constexpr (!BWD) {
+        // alpha~_t = ((alpha~_{t-1} kappa) * b + alpha~_{t-1}[u] q) / c_{t-1} * b_t ;  c_{t-1} = band sum + dense element
+        const float tot = sband + xd;
+        if (lane == 0) pc[t - 1] = tot;
+        const float inv = vrcp_pos(tot);
+        const float add = xd * q_out;
+#pragma unroll
+        for (int n = 0; n < vNJ; ++n) v[n] = kap[n] > 0.f ? ((acc[n] + add) * inv) * e[n] : 0.f;
+        xdn = has_d ? (fmaf(sband, r_in, xd * a_uu) * inv) * ed : 0.f;
+#pragma unroll
+        for (int n = 0; n < vNJ; ++n) o[n] = v[n];
+        out_d = xdn;
+      } else {
+        // beta_t = (kappa (b * w_{t+1}) + r w_{t+1}[u]) / c_{t+1}  (1 at the clip's last frame);  gamma_t = alpha~_t / c_t beta_t
+        const float ct = cnext;
+        if (t > 0) cnext = pc[t - 1];
+        const float invc = vrcp_pos(ct), invn = vrcp_pos(cprev);
+        const bool last = it == 0;
+        const float add = xd * r_in;
+        const float4* al4 = reinterpret_cast<const float4*>(in + vMaxS) + 3 * lane;
+        const float ald = has_d ? in[vMaxS + jd] : 0.f;
+#pragma unroll
+        for (int m = 0; m < vNJ / 4; ++m) {
+          const float4 x = al4[m];
+          const float al[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int n = 4 * m + k;
+            const float be = last ? 1.f : fmaf(kap[n], acc[n], add) * invn;
+            o[n] = (al[k] * invc) * be;
+            v[n] = kap[n] > 0.f ? e[n] * be : 0.f;
+          }
+        }
+        const float bed = last ? 1.f : fmaf(sband, q_out, xd * a_uu) * invn;
+        out_d = (ald * invc) * bed;
+        xdn = has_d ? ed * bed : 0.f;
+        cprev = ct;
+      }
+    }
+    // the new vector -> the row the next sweep reads (forward: scaled by kappa), the output -> the scratch row
+    float ss = 0.f;
+#pragma unroll
+    for (int n = 0; n < vNJ; ++n) ss += v[n];
+    float* rown = s_row + buf * vRow + vDP;
+#pragma unroll
+    for (int m = 0; m < vNJ / 4; ++m) {
+      float4 u;
+      if (BWD) u = make_float4(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3]);
+      else u = make_float4(v[4 * m] * kap[4 * m], v[4 * m + 1] * kap[4 * m + 1], v[4 * m + 2] * kap[4 * m + 2], v[4 * m + 3] * kap[4 * m + 3]);
+      reinterpret_cast<float4*>(rown)[3 * lane + m] = u;
+      reinterpret_cast<float4*>(s_out)[3 * lane + m] = make_float4(o[4 * m], o[4 * m + 1], o[4 * m + 2], o[4 * m + 3]);
+    }
+    sband = vwarp_sum(ss);
+    xd = xdn;
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < vNJ; ++n)
+      if (cp_ok[n]) st_global_cs_f32(pout + 32 * n, s_out[lane + 32 * n]);
+    if (has_d && lane == 0) st_global_cs_f32(pout + jd, out_d);
+    pout += dS;
+  }
+  if (!BWD && lane == 0) pc[len - 1] = sband + xd;
+}
+
+// vit_fb_banded.cu calls these
+int fb_conv_detect(const float* A, int S, const vit_structure* st, int Dt, void* params, cudaStream_t stream) {
+  const char* e = getenv("VIT_FB_CONV");
+  const int enable = !(e && e[0] == '0');
+  fb_conv_detect_kernel<<<1, vMaxS, 0, stream>>>(A, S, st->dense_index, st->halfwidth, Dt, enable, (ConvParams*)params);
+  note_launch();
+  VIT_CUDA_TRY(cudaGetLastError());
+  return VIT_OK;
+}
+
+int fb_conv_passes(int D, const void* params, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max,
+                   int S, int jd, float* gamma, float* cnorm, cudaStream_t stream) {
+  const size_t smem_f = (size_t)(2 * vRow + vStages * 1 * vMaxS + vMaxS) * sizeof(float);
+  const size_t smem_b = (size_t)(2 * vRow + vStages * 2 * vMaxS + vMaxS) * sizeof(float);
+#define VIT_FBC_CASE(DD)                                                                                            \
+  case DD: {                                                                                                        \
+    fb_conv_pass_kernel<DD, false><<<B, 32, smem_f, stream>>>((const ConvParams*)params, pi, lik, lengths, T_max, S, jd, \
+                                                              gamma, cnorm);                                        \
+    fb_conv_pass_kernel<DD, true><<<B, 32, smem_b, stream>>>((const ConvParams*)params, pi, lik, lengths, T_max, S, jd, \
+                                                             gamma, cnorm);                                         \
+  } break;
+  switch (D) {
+    VIT_FBC_CASE(4) VIT_FBC_CASE(8) VIT_FBC_CASE(12) VIT_FBC_CASE(14)
+    default: return VIT_ERR_UNSUPPORTED_ALGO;
+  }
+#undef VIT_FBC_CASE
+  note_launch(2);
+  VIT_CUDA_TRY(cudaGetLastError());
+  return VIT_OK;
+}
+
+}  // namespace vit
