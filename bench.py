@@ -282,11 +282,11 @@ def leg_forward_backward(dev, world, barrier, all_max, peaks, steps=3):
 
     hbm = float(peaks.get('hbm_gbs', 6650.0))
     bytes_ = 20.0 * B * T * S           # b read twice, alpha~ written and read, gamma written
-    # the structured fast path first (what impl='auto' takes for this matrix: band +-14 + the unvoiced state, exact
-    # zeros elsewhere -- S (2d+3) instead of S^2 multiply-adds per frame, plain fp32 FFMA), then the headline: the dense
-    # tcgen05 kernel config 4 names, whose results stay in gamma / ll for the parity check below
+    # the structured fast path first (what impl='auto' takes for this matrix: band +-14 built from one jump histogram +
+    # the unvoiced state, exact zeros elsewhere -- S (2d+3) instead of S^2 multiply-adds per frame, plain fp32 FFMA),
+    # then the headline: the dense tcgen05 kernel config 4 names, whose results stay in gamma / ll for the parity check
     ms_b, launches_b = timed('banded')
-    structured = {'impl': 'banded', 'ms_per_step': ms_b, 'value': world * B * T / (ms_b * 1e-3), 'unit': UNIT,
+    structured = {'impl': 'banded (scaled-Toeplitz band as a convolution, one warp per clip: csrc/vit_fb_conv.cu)', 'ms_per_step': ms_b, 'value': world * B * T / (ms_b * 1e-3), 'unit': UNIT,
                   'gpu_launches': int(launches_b), 'halfwidth': 14, 'dtype': 'f32 (FFMA)',
                   'roofline_hbm': {'bound': 'hbm', 'achieved': bytes_ / (ms_b * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
                                    'frac': bytes_ / (ms_b * 1e-3) / 1e9 / hbm, 'algorithmic_bytes': bytes_},

@@ -116,13 +116,13 @@ __global__ void fb_conv_detect_kernel(const float* __restrict__ A, int S, int jd
 }
 
 __device__ __forceinline__ float vrcp_pos(float x) {        // as frcp_pos in vit_fb_banded.cu
-  float r;
+  // branch-free (a branch here would split the step into basic blocks the scheduler cannot interleave across): the
+  // direct reciprocal for normal x, the one rescaled by 2^64 either side for denormal x, 0 for x == 0
+  float r, r2;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  if (x < 1.1754944e-38f) {
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 18446744073709551616.f));
-    r = x > 0.f ? r * 18446744073709551616.f : 0.f;
-  }
-  return r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r2) : "f"(x * 18446744073709551616.f));
+  r2 = x > 0.f ? r2 * 18446744073709551616.f : 0.f;
+  return x < 1.1754944e-38f ? r2 : r;
 }
 __device__ __forceinline__ float vwarp_sum(float v) {
 #pragma unroll
@@ -130,8 +130,10 @@ __device__ __forceinline__ float vwarp_sum(float v) {
   return v;
 }
 
-// One warp (= one block) per clip.
-template <int D, bool BWD>
+// One warp (= one block) per clip.  NF >= 0: the host promises that the band states are exactly [0, Sv) (dense state last or
+// absent), Sv in (32 NF, 32 NF + 32]: element rows n < NF of the lane-contiguous layout need no predicate, row NF one
+// compare, rows past it do not exist.  NF = -1: any layout, every element predicated.
+template <int D, bool BWD, int NF>
 __global__ void __launch_bounds__(32, 16)
 fb_conv_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict__ pi, const float* __restrict__ lik,
                     const int32_t* __restrict__ lengths, int T_max, int S, int jd, float* __restrict__ gamma,
@@ -145,6 +147,7 @@ fb_conv_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict_
   float* s_row = sm;                                  // [2][vRow]: the vector the sweep reads (forward: alpha~ kappa, backward: w)
   float* s_in = sm + 2 * vRow;                        // [vStages][KINDS][vMaxS]: b_t (and alpha~_t) rows, fetched by cp.async
   float* s_out = s_in + vStages * KINDS * vMaxS;      // [vMaxS]: this step's output row on its way to HBM
+  __shared__ float s_ind[vStages][3];                 // the dense state's b_t and alpha~_t (never part of a staged row), c_t
 
   const int lane = threadIdx.x;
   const int b = blockIdx.x;
@@ -165,127 +168,61 @@ fb_conv_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict_
   __syncwarp();
 
   // lane-contiguous element ownership for everything that touches HBM: lane l moves elements l + 32 n of a row
-  bool cp_ok[vNJ];
-#pragma unroll
-  for (int n = 0; n < vNJ; ++n) cp_ok[n] = lane + 32 * n < S && lane + 32 * n != jd;
+  const int Sv = has_d ? S - 1 : S;                    // (NF >= 0 only) band states are [0, Sv)
+  auto elem_ok = [&](int n) {
+    if constexpr (NF >= 0) return n < NF || (n == NF && lane + 32 * NF < Sv);
+    else return lane + 32 * n < S && lane + 32 * n != jd;
+  };
+  constexpr int NROWS = NF >= 0 ? NF + 1 : vNJ;        // element rows that can hold a band state
   const long long dS = BWD ? -(long long)S : (long long)S;
   const long long gamma_delta = reinterpret_cast<const char*>(gamma) - reinterpret_cast<const char*>(lik);
   const float* pin = lik + ((size_t)b * T_max + (BWD ? len - 1 : 0)) * S + lane;     // row staged next
   float* pout = gamma + ((size_t)b * T_max + (BWD ? len - 1 : 0)) * S + lane;        // row written next
   float* pc = cnorm + (size_t)b * T_max;
 
-  // requests the input rows of step it_f into stage buffer it_f % vStages (the dense state's slot is copied like any
-  // other and read as a scalar; it never enters the vector row the sweep reads)
+  // requests the input rows of step it_f into stage buffer it_f % vStages.  The slots of a staged row that hold no band
+  // state (the dense state's, those past S) are never written and stay 0, so whatever is multiplied by them is 0: no
+  // masks in the step.  The dense state's inputs go to s_ind (lane 0).
   auto stage = [&](int it_f) {
     if (it_f < len) {
-      float* dst = s_in + (it_f % vStages) * KINDS * vMaxS + lane;
+      const int sb = it_f % vStages;
+      float* dst = s_in + sb * KINDS * vMaxS + lane;
       const uint32_t d0 = smem_u32(dst), d1 = smem_u32(dst + (KINDS - 1) * vMaxS);
       const float* srca = reinterpret_cast<const float*>(reinterpret_cast<const char*>(pin) + gamma_delta);
 #pragma unroll
-      for (int n = 0; n < vNJ; ++n)
-        if (lane + 32 * n < S) {                         // (the dense state's slot is copied too: read as a scalar below)
+      for (int n = 0; n < NROWS; ++n)
+        if (elem_ok(n)) {
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 128 * n), "l"(pin + 32 * n) : "memory");
           if (BWD) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d1 + 128 * n), "l"(srca + 32 * n) : "memory");
         }
+      if (BWD && lane == 1)                                // c_t of that step (t = len - 1 - it_f)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s_ind[sb][2])), "l"(pc + (len - 1 - it_f)) : "memory");
+      if (has_d && lane == 0) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s_ind[sb][0])), "l"(pin + jd) : "memory");
+        if (BWD) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s_ind[sb][1])), "l"(srca + jd) : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     pin += dS;
   };
   stage(0);
   stage(1);
+  stage(2);
 
   float xd = 0.f;          // the dense state's value of the previous step (forward: alpha~_{t-1}[u]; backward: w_{t+1}[u])
-  float sband = 0.f;       // sum over the band states of the previous step's vector
+  float ss = 0.f;          // my lane's part of the sum over the band states of the previous step's vector: reduced over
+                           // the warp at the START of the next step, so the shuffle chain hides under the sweep's FFMAs
   float cprev = 1.f;       // backward: c_{t+1}
-  float cnext = BWD ? pc[len - 1] : 0.f;                   // backward: c_t of the coming step, loaded one step ahead
-  const int n_steps = len;
-  for (int it = 0; it < n_steps; ++it) {
-    const int t = BWD ? len - 1 - it : it;
-    const int buf = it & 1;
-    stage(it + 2);
-    asm volatile("cp.async.wait_group 2;" ::: "memory");
-    __syncwarp();
-    const float* in = s_in + (it % vStages) * KINDS * vMaxS;
-    // my 12 states' inputs (the dense state's slot and the slots past S count for nothing: kappa = 0, masks below)
-    float e[vNJ];
+
+  // the end of a step: the new vector -> the row the next sweep reads (forward: scaled by kappa), the output -> the
+  // scratch row -> HBM in the lane-contiguous layout; the inputs of step it + 3 are requested between the scratch reads
+  // and the stores (in-order issue: their latencies overlap)
+  auto finish_step = [&](int it, const float* v, const float* o, float xdn, float out_d) {
+    float s = 0.f;
 #pragma unroll
-    for (int m = 0; m < vNJ / 4; ++m) {
-      const float4 x = reinterpret_cast<const float4*>(in)[3 * lane + m];
-      e[4 * m] = x.x; e[4 * m + 1] = x.y; e[4 * m + 2] = x.z; e[4 * m + 3] = x.w;
-    }
-    const float ed = has_d ? in[jd] : 0.f;
-    float v[vNJ], xdn, out_d;                              // the new vector, its dense element, the dense element's output
-    float o[vNJ];                                          // what goes to HBM
-    if (!BWD && it == 0) {
-      // alpha~_0 = pi * b_0
-#pragma unroll
-      for (int n = 0; n < vNJ; ++n) v[n] = kap[n] > 0.f ? pi[j0 + n] * e[n] : 0.f;
-      xdn = has_d ? pi[jd] * ed : 0.f;
-#pragma unroll
-      for (int n = 0; n < vNJ; ++n) o[n] = v[n];
-      out_d = xdn;
-    } else {
-      // the band: acc[out] = sum_in row[in] tap[(out - in) + D]
-      float acc[vNJ];
-#pragma unroll
-      for (int n = 0; n < vNJ; ++n) acc[n] = 0.f;
-      const float4* row4 = reinterpret_cast<const float4*>(s_row + (buf ^ 1) * vRow) + 3 * lane;
-#pragma unroll
-      for (int m = M0; m <= M1; ++m) {
-        const float4 x = row4[m];
-        const float wv[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int n = 0; n < vNJ; ++n) {
-            const int rr = n - (4 * m + k) + vDP + D;      // in = 12 lane + 4 m + k - vDP, out = 12 lane + n
-            if (rr >= 0 && rr < W) acc[n] = fmaf(wv[k], tap[rr], acc[n]);
-          }
-      }
-      if constexpr (!BWD) {
-        // alpha~_t = ((alpha~_{t-1} kappa) * b + alpha~_{t-1}[u] q) / c_{t-1} * b_t ;  c_{t-1} = band sum + dense element
-        const float tot = sband + xd;
-        if (lane == 0) pc[t - 1] = tot;
-        const float inv = vrcp_pos(tot);
-        const float add = xd * q_out;
-#pragma unroll
-        for (int n = 0; n < vNJ; ++n) v[n] = kap[n] > 0.f ? ((acc[n] + add) * inv) * e[n] : 0.f;
-        xdn = has_d ? (fmaf(sband, r_in, xd * a_uu) * inv) * ed : 0.f;
-#pragma unroll
-        for (int n = 0; n < vNJ; ++n) o[n] = v[n];
-        out_d = xdn;
-      } else {
-        // beta_t = (kappa (b * w_{t+1}) + r w_{t+1}[u]) / c_{t+1}  (1 at the clip's last frame);  gamma_t = alpha~_t / c_t beta_t
-        const float ct = cnext;
-        if (t > 0) cnext = pc[t - 1];
-        const float invc = vrcp_pos(ct), invn = vrcp_pos(cprev);
-        const bool last = it == 0;
-        const float add = xd * r_in;
-        const float4* al4 = reinterpret_cast<const float4*>(in + vMaxS) + 3 * lane;
-        const float ald = has_d ? in[vMaxS + jd] : 0.f;
-#pragma unroll
-        for (int m = 0; m < vNJ / 4; ++m) {
-          const float4 x = al4[m];
-          const float al[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int n = 4 * m + k;
-            const float be = last ? 1.f : fmaf(kap[n], acc[n], add) * invn;
-            o[n] = (al[k] * invc) * be;
-            v[n] = kap[n] > 0.f ? e[n] * be : 0.f;
-          }
-        }
-        const float bed = last ? 1.f : fmaf(sband, q_out, xd * a_uu) * invn;
-        out_d = (ald * invc) * bed;
-        xdn = has_d ? ed * bed : 0.f;
-        cprev = ct;
-      }
-    }
-    // the new vector -> the row the next sweep reads (forward: scaled by kappa), the output -> the scratch row
-    float ss = 0.f;
-#pragma unroll
-    for (int n = 0; n < vNJ; ++n) ss += v[n];
-    float* rown = s_row + buf * vRow + vDP;
+    for (int n = 0; n < vNJ; ++n) s += v[n];
+    ss = s;
+    float* rown = s_row + (it & 1) * vRow + vDP;
 #pragma unroll
     for (int m = 0; m < vNJ / 4; ++m) {
       float4 u;
@@ -294,16 +231,104 @@ fb_conv_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict_
       reinterpret_cast<float4*>(rown)[3 * lane + m] = u;
       reinterpret_cast<float4*>(s_out)[3 * lane + m] = make_float4(o[4 * m], o[4 * m + 1], o[4 * m + 2], o[4 * m + 3]);
     }
-    sband = vwarp_sum(ss);
     xd = xdn;
     __syncwarp();
+    float og[NROWS];
 #pragma unroll
-    for (int n = 0; n < vNJ; ++n)
-      if (cp_ok[n]) st_global_cs_f32(pout + 32 * n, s_out[lane + 32 * n]);
+    for (int n = 0; n < NROWS; ++n) og[n] = s_out[lane + 32 * n];
+    stage(it + 3);
+#pragma unroll
+    for (int n = 0; n < NROWS; ++n)
+      if (elem_ok(n)) st_global_cs_f32(pout + 32 * n, og[n]);
     if (has_d && lane == 0) st_global_cs_f32(pout + jd, out_d);
     pout += dS;
+  };
+  auto step_inputs = [&](int it, float* e, float& ed) {
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncwarp();
+    const float* in = s_in + (it % vStages) * KINDS * vMaxS;
+#pragma unroll
+    for (int m = 0; m < vNJ / 4; ++m) {
+      const float4 x = reinterpret_cast<const float4*>(in)[3 * lane + m];
+      e[4 * m] = x.x; e[4 * m + 1] = x.y; e[4 * m + 2] = x.z; e[4 * m + 3] = x.w;
+    }
+    ed = has_d ? s_ind[it % vStages][0] : 0.f;
+    return in;
+  };
+
+  if constexpr (!BWD) {
+    // step 0: alpha~_0 = pi * b_0
+    float e[vNJ], ed, v[vNJ];
+    step_inputs(0, e, ed);
+#pragma unroll
+    for (int n = 0; n < vNJ; ++n) v[n] = j0 + n < S ? pi[j0 + n] * e[n] : 0.f;
+    const float xdn = has_d ? pi[jd] * ed : 0.f;
+    finish_step(0, v, v, xdn, xdn);
   }
-  if (!BWD && lane == 0) pc[len - 1] = sband + xd;
+  for (int it = BWD ? 0 : 1; it < len; ++it) {
+    const int t = BWD ? len - 1 - it : it;
+    float e[vNJ], ed;
+    const float* in = step_inputs(it, e, ed);
+    const float sband = vwarp_sum(ss);                     // sum over the band states of the previous step's vector
+    // the band: acc[out] = sum_in row[in] tap[(out - in) + D]  (forward: on top of the dense state's contribution)
+    float acc[vNJ];
+    const float acc0 = BWD ? 0.f : xd * q_out;
+#pragma unroll
+    for (int n = 0; n < vNJ; ++n) acc[n] = acc0;
+    const float4* row4 = reinterpret_cast<const float4*>(s_row + ((it & 1) ^ 1) * vRow) + 3 * lane;
+#pragma unroll
+    for (int m = M0; m <= M1; ++m) {
+      const float4 x = row4[m];
+      const float wv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int n = 0; n < vNJ; ++n) {
+          const int rr = n - (4 * m + k) + vDP + D;        // in = 12 lane + 4 m + k - vDP, out = 12 lane + n
+          if (rr >= 0 && rr < W) acc[n] = fmaf(wv[k], tap[rr], acc[n]);
+        }
+    }
+    float v[vNJ], o[vNJ], xdn, out_d;
+    if constexpr (!BWD) {
+      // alpha~_t = ((alpha~_{t-1} kappa) * b + alpha~_{t-1}[u] q) / c_{t-1} * b_t ;  c_{t-1} = band sum + dense element
+      const float tot = sband + xd;
+      if (lane == 0) pc[t - 1] = tot;
+      const float inv = vrcp_pos(tot);
+#pragma unroll
+      for (int n = 0; n < vNJ; ++n) o[n] = v[n] = (acc[n] * inv) * e[n];
+      xdn = has_d ? (fmaf(sband, r_in, xd * a_uu) * inv) * ed : 0.f;
+      out_d = xdn;
+    } else {
+      // beta_t = (kappa (b * w_{t+1}) + r w_{t+1}[u]) / c_{t+1}  (1 at the clip's last frame);  gamma_t = alpha~_t / c_t beta_t
+      const float ct = s_ind[it % vStages][2];
+      const float invc = vrcp_pos(ct), invn = vrcp_pos(cprev);
+      const bool last = it == 0;
+      const float add = xd * r_in;
+      const float4* al4 = reinterpret_cast<const float4*>(in + vMaxS) + 3 * lane;
+      const float ald = has_d ? s_ind[it % vStages][1] : 0.f;
+#pragma unroll
+      for (int m = 0; m < vNJ / 4; ++m) {
+        const float4 x = al4[m];
+        const float al[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int n = 4 * m + k;
+          const float be = last ? 1.f : fmaf(kap[n], acc[n], add) * invn;
+          o[n] = (al[k] * invc) * be;
+          v[n] = e[n] * be;
+        }
+      }
+      const float bed = last ? 1.f : fmaf(sband, q_out, xd * a_uu) * invn;
+      out_d = (ald * invc) * bed;
+      xdn = has_d ? ed * bed : 0.f;
+      cprev = ct;
+    }
+    finish_step(it, v, o, xdn, out_d);
+  }
+  if (!BWD) {
+    const float sband = vwarp_sum(ss);
+    if (lane == 0) pc[len - 1] = sband + xd;
+  }
 }
 
 // vit_fb_banded.cu calls these
@@ -320,17 +345,29 @@ int fb_conv_passes(int D, const void* params, const float* pi, const float* lik,
                    int S, int jd, float* gamma, float* cnorm, cudaStream_t stream) {
   const size_t smem_f = (size_t)(2 * vRow + vStages * 1 * vMaxS + vMaxS) * sizeof(float);
   const size_t smem_b = (size_t)(2 * vRow + vStages * 2 * vMaxS + vMaxS) * sizeof(float);
-#define VIT_FBC_CASE(DD)                                                                                            \
-  case DD: {                                                                                                        \
-    fb_conv_pass_kernel<DD, false><<<B, 32, smem_f, stream>>>((const ConvParams*)params, pi, lik, lengths, T_max, S, jd, \
-                                                              gamma, cnorm);                                        \
-    fb_conv_pass_kernel<DD, true><<<B, 32, smem_b, stream>>>((const ConvParams*)params, pi, lik, lengths, T_max, S, jd, \
-                                                             gamma, cnorm);                                         \
-  } break;
+  // NF: the element-row specialisation (see the kernel).  Instances exist for the two layouts the reference's state sets
+  // have -- band states [0, Sv) with Sv in (288, 320] (dcnet: 320 bins) or (352, 384] (tonet / ftanet: 360) -- else generic.
+  const int Sv = jd >= 0 ? S - 1 : S;
+  const bool tail_dense = jd < 0 || jd == S - 1;
+  const int nf = (tail_dense && Sv > 0) ? (Sv - 1) / 32 : -1;
+#define VIT_FBC_LAUNCH(DD, NFF)                                                                                      \
+  do {                                                                                                               \
+    fb_conv_pass_kernel<DD, false, NFF><<<B, 32, smem_f, stream>>>((const ConvParams*)params, pi, lik, lengths, T_max, S, \
+                                                                   jd, gamma, cnorm);                               \
+    fb_conv_pass_kernel<DD, true, NFF><<<B, 32, smem_b, stream>>>((const ConvParams*)params, pi, lik, lengths, T_max, S,  \
+                                                                  jd, gamma, cnorm);                                \
+  } while (0)
+#define VIT_FBC_CASE(DD)                                                                                             \
+  case DD:                                                                                                           \
+    if (nf == 11) VIT_FBC_LAUNCH(DD, 11);                                                                            \
+    else if (nf == 9) VIT_FBC_LAUNCH(DD, 9);                                                                       \
+    else VIT_FBC_LAUNCH(DD, -1);                                                                                     \
+    break;
   switch (D) {
     VIT_FBC_CASE(4) VIT_FBC_CASE(8) VIT_FBC_CASE(12) VIT_FBC_CASE(14)
     default: return VIT_ERR_UNSUPPORTED_ALGO;
   }
+#undef VIT_FBC_LAUNCH
 #undef VIT_FBC_CASE
   note_launch(2);
   VIT_CUDA_TRY(cudaGetLastError());
