@@ -107,8 +107,8 @@ def test_auto_takes_the_banded_kernel_and_agrees_with_the_dense_ones(FB, cuda_li
     lik = np.exp(rng.standard_normal((9, 50, 361))).astype(np.float32)
     n0 = _lib.launch_count()
     g_auto, ll_auto = FB(A, pi).run_host(lik)
-    # form check + two convolution passes + two general banded passes (which return at once here) + log L
-    assert _lib.launch_count() - n0 == 6
+    # form check + two convolution passes + their log L + two general banded passes and their log L (which return at once)
+    assert _lib.launch_count() - n0 == 7
     g_b, ll_b = FB(A, pi, impl='banded').run_host(lik)
     assert np.array_equal(g_auto, g_b) and np.array_equal(ll_auto, ll_b)
     for impl in ('tc', 'simt'):
@@ -167,6 +167,27 @@ def test_scaled_toeplitz_matrices_take_the_convolution_kernels(FB, n_bins, d, de
     L = rng.integers(0, T + 1, size=B).astype(np.int32)
     L[:3] = [T, 1, 0][:min(3, B)]
     assert run_both_forms(FB, A, pi, lik, L)
+
+
+@pytest.mark.parametrize('n_bins,d,dense,T,B', [(721, 40, 'last', 24, 9), (721, 56, 'last', 18, 5), (721, 33, 'last', 12, 3),
+                                                 (600, 20, None, 15, 4), (767, 28, 'last', 10, 3), (499, 40, 'first', 12, 4)])
+def test_wide_bands_722_state_sets_take_the_wide_convolution_kernels(FB, n_bins, d, dense, T, B):
+    """jdc (+-40 of 721 bins) and the imm HMM (+-56): two runs of 12 states per lane, taps in shared memory.  With the
+    form check switched off the same call goes to the dense FFMA kernel."""
+    rng = np.random.default_rng(n_bins + d)
+    A, pi = toeplitz_hmm(n_bins, d, dense, rng)
+    S = len(pi)
+    lik = peaky_likelihoods(B, T, S, rng) if d == 40 else np.exp(2 * rng.standard_normal((B, T, S))).astype(np.float32)
+    L = rng.integers(0, T + 1, size=B).astype(np.int32)
+    L[:3] = [T, 1, 0]
+    assert run_both_forms(FB, A, pi, lik, L)
+
+
+def test_wide_general_band_falls_back_to_the_dense_kernel(FB):
+    rng = np.random.default_rng(12)
+    A, pi = banded_hmm(722, 30, 721, rng)
+    lik = np.exp(rng.standard_normal((4, 12, 722))).astype(np.float32)
+    assert not run_both_forms(FB, A, pi, lik)
 
 
 def test_general_band_does_not_take_the_convolution_kernels(FB):

@@ -64,7 +64,7 @@ size_t fb_workspace_bytes(int B, int T_max, int S);
 bool fb_supported(int S);
 int fb_run(const float* A, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S,
            void* workspace, size_t workspace_bytes, float* gamma, float* loglik, cudaEvent_t ev0, cudaEvent_t ev1,
-           cudaStream_t stream);
+           cudaStream_t stream, const int* skip = nullptr);
 
 // vit_emis.cu
 int emissions_run(const float* logits, const float* prior, int B, int T, int n_bins, int model, int spw, float threshold,
@@ -91,7 +91,7 @@ int fb_tc_run(const float* A, const float* pi, const float* lik, const int32_t* 
               void* workspace, size_t workspace_bytes, float* gamma, float* loglik, cudaStream_t stream);
 // vit_fb_banded.cu
 bool fb_banded_supported(int S, const vit_structure* st);
-size_t fb_banded_workspace_bytes(int B, int T_max);
+size_t fb_banded_extra_bytes(int B, int T_max);
 int fb_banded_run(const float* A, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S,
                   const vit_structure* st, void* workspace, size_t workspace_bytes, float* gamma, float* loglik,
                   cudaStream_t stream);
@@ -289,7 +289,8 @@ int vit_fb_workspace_bytes(int B, int T_max, int S, size_t* out_bytes) {
   if (!fb_supported(S) && !fb_tc_supported(S)) return VIT_ERR_UNSUPPORTED_ALGO;
   const size_t a = fb_supported(S) ? fb_workspace_bytes(B, T_max, S) : 0;
   const size_t b = fb_tc_supported(S) ? fb_tc_workspace_bytes(B, T_max, S) : 0;
-  *out_bytes = a > b ? a : b;
+  // + the structured kernels' own normalisers and parameter block (they may run next to the dense FFMA fall-back)
+  *out_bytes = (a > b ? a : b) + fb_banded_extra_bytes(B, T_max);
   return VIT_OK;
 }
 

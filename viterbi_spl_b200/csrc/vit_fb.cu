@@ -46,7 +46,9 @@ template <int NJ, bool BWD>
 __global__ void __launch_bounds__(tThreads, 1)
 fb_pass_kernel(const float* __restrict__ packedT, const float* __restrict__ packedS, const float* __restrict__ pi,
                const float* __restrict__ lik, const int32_t* __restrict__ lengths, int B, int T_max, int S,
-               TmemPlan p, float* __restrict__ gamma, float* __restrict__ cnorm, int dev) {
+               TmemPlan p, float* __restrict__ gamma, float* __restrict__ cnorm, int dev, const int* __restrict__ skip) {
+  // (skip: the verdict of fb_conv_detect_kernel when this kernel is the fall-back of the convolution kernels)
+  if (skip && *skip) return;
   constexpr int MB = tMB, KS = tKS, NC = NJ * 4;
   constexpr int NPAD = 8 * NJ;
   extern __shared__ __align__(128) float smem[];
@@ -331,7 +333,8 @@ fb_pass_kernel(const float* __restrict__ packedT, const float* __restrict__ pack
 
 // log L = sum_t log c_t : one warp per clip, double accumulation (shared with vit_fb_tc.cu)
 __global__ void fb_loglik_kernel(const float* __restrict__ cnorm, const int32_t* __restrict__ lengths, int B, int T_max,
-                                 float* __restrict__ loglik) {
+                                 float* __restrict__ loglik, const int* __restrict__ flag, int want) {
+  if (flag && *flag != want) return;               // (one of two alternative kernel sets ran: only its normalisers count)
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
   const int len = lengths ? lengths[b] : T_max;
@@ -360,7 +363,7 @@ size_t fb_workspace_bytes(int B, int T_max, int S) {
 template <int NJ>
 static int launch_fb(const TmemPlan& p, const float* pT_f, const float* pS_f, const float* pT_b, const float* pS_b,
                      const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S, float* gamma,
-                     float* cnorm, cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t stream) {
+                     float* cnorm, cudaEvent_t ev0, cudaEvent_t ev1, cudaStream_t stream, const int* skip) {
   size_t smem = tmem_smem_bytes(p);
   if (smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM (each allocates all 512 TMEM columns), see vit_tmem.cu
   auto kf = fb_pass_kernel<NJ, false>;
@@ -391,9 +394,9 @@ static int launch_fb(const TmemPlan& p, const float* pT_f, const float* pS_f, co
   const int n_clusters = want < max_clusters ? want : max_clusters;
   cfg.gridDim = dim3(n_clusters * p.C);
   if (ev0) VIT_CUDA_TRY(cudaEventRecord(ev0, stream));
-  VIT_CUDA_TRY(cudaLaunchKernelEx(&cfg, kf, pT_f, pS_f, pi, lik, lengths, B, T_max, S, p, gamma, cnorm, 0));
+  VIT_CUDA_TRY(cudaLaunchKernelEx(&cfg, kf, pT_f, pS_f, pi, lik, lengths, B, T_max, S, p, gamma, cnorm, 0, skip));
   note_launch();
-  VIT_CUDA_TRY(cudaLaunchKernelEx(&cfg, kb, pT_b, pS_b, pi, lik, lengths, B, T_max, S, p, gamma, cnorm, 0));
+  VIT_CUDA_TRY(cudaLaunchKernelEx(&cfg, kb, pT_b, pS_b, pi, lik, lengths, B, T_max, S, p, gamma, cnorm, 0, skip));
   note_launch();
   if (ev1) VIT_CUDA_TRY(cudaEventRecord(ev1, stream));
   return VIT_OK;
@@ -401,7 +404,7 @@ static int launch_fb(const TmemPlan& p, const float* pT_f, const float* pS_f, co
 
 int fb_run(const float* A, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S,
            void* workspace, size_t workspace_bytes, float* gamma, float* loglik, cudaEvent_t ev0, cudaEvent_t ev1,
-           cudaStream_t stream) {
+           cudaStream_t stream, const int* skip) {
   TmemPlan p;
   if (!make_fb_plan(S, &p)) return VIT_ERR_UNSUPPORTED_ALGO;
   if (workspace_bytes < fb_workspace_bytes(B, T_max, S)) return VIT_ERR_WORKSPACE_TOO_SMALL;
@@ -416,8 +419,9 @@ int fb_run(const float* A, const float* pi, const float* lik, const int32_t* len
     ws += align_up(tmem_tail_floats(p) * sizeof(float) + 16, 256);
   }
   float* cnorm = (float*)ws;
-  // frames past a clip's length carry gamma = 0
-  if (lengths) VIT_CUDA_TRY(cudaMemsetAsync(gamma, 0, (size_t)B * T_max * S * sizeof(float), stream));
+  // frames past a clip's length carry gamma = 0 (as a fall-back -- skip != NULL -- the caller has done it, and gamma may
+  // already hold the other kernel set's result)
+  if (lengths && !skip) VIT_CUDA_TRY(cudaMemsetAsync(gamma, 0, (size_t)B * T_max * S * sizeof(float), stream));
   {
     const size_t total = tmem_packed_floats(p) + tmem_tail_floats(p);
     const int grid = (int)((total + 255) / 256);
@@ -432,7 +436,7 @@ int fb_run(const float* A, const float* pi, const float* lik, const int32_t* len
   switch (p.NJ) {
 #define VIT_FB_CASE(N)                                                                                             \
   case N:                                                                                                          \
-    rc = launch_fb<N>(p, pT[0], pS[0], pT[1], pS[1], pi, lik, lengths, B, T_max, S, gamma, cnorm, ev0, ev1, stream); \
+    rc = launch_fb<N>(p, pT[0], pS[0], pT[1], pS[1], pi, lik, lengths, B, T_max, S, gamma, cnorm, ev0, ev1, stream, skip); \
     break;
     VIT_FB_CASE(1) VIT_FB_CASE(2) VIT_FB_CASE(3) VIT_FB_CASE(4) VIT_FB_CASE(5) VIT_FB_CASE(6)
 #undef VIT_FB_CASE
@@ -440,7 +444,7 @@ int fb_run(const float* A, const float* pi, const float* lik, const int32_t* len
   }
   if (rc != VIT_OK) return rc;
   if (loglik) {
-    fb_loglik_kernel<<<(B + 3) / 4, 128, 0, stream>>>(cnorm, lengths, B, T_max, loglik);
+    fb_loglik_kernel<<<(B + 3) / 4, 128, 0, stream>>>(cnorm, lengths, B, T_max, loglik, skip, 0);
     note_launch();
     VIT_CUDA_TRY(cudaGetLastError());
   }

@@ -430,7 +430,12 @@ fb_banded_pass_kernel(const float* __restrict__ A, const float* __restrict__ pi,
 
 // vit_fb.cu
 __global__ void fb_loglik_kernel(const float* __restrict__ cnorm, const int32_t* __restrict__ lengths, int B, int T_max,
-                                 float* __restrict__ loglik);
+                                 float* __restrict__ loglik, const int* __restrict__ flag, int want);
+bool fb_supported(int S);
+size_t fb_workspace_bytes(int B, int T_max, int S);
+int fb_run(const float* A, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S,
+           void* workspace, size_t workspace_bytes, float* gamma, float* loglik, cudaEvent_t ev0, cudaEvent_t ev1,
+           cudaStream_t stream, const int* skip);
 
 static int fb_banded_template_D(int d) {
   const int opts[] = {4, 8, 12, 14};
@@ -438,43 +443,64 @@ static int fb_banded_template_D(int d) {
   return -1;
 }
 
-// `st` describes the PROBABILITY-domain matrix (vit_analyze_structure_f32 on A; the band and the dense state are the same
-// whichever way round the matrix is stored): band + one dense state, every other entry exactly 0
-bool fb_banded_supported(int S, const vit_structure* st) {
-  if (!st || st->kind != 1) return false;
-  if (st->background != 0.f) return false;
-  if (S > fMaxS || S < 2) return false;
-  if (st->dense_index < -1 || st->dense_index >= S) return false;
-  return fb_banded_template_D(st->halfwidth) > 0;
-}
-
 // vit_fb_conv.cu: the scaled-Toeplitz form (what the reference's builders produce) as a convolution, one warp per clip
 size_t fb_conv_params_bytes();
+int fb_conv_template_D(int S, int d);
 int fb_conv_detect(const float* A, int S, const vit_structure* st, int Dt, void* params, cudaStream_t stream);
 int fb_conv_passes(int D, const void* params, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max,
                    int S, int jd, float* gamma, float* cnorm, cudaStream_t stream);
 
+// general band kernel of this file: S <= 384, d <= 14
+static bool fb_banded_narrow(int S, const vit_structure* st) { return S <= fMaxS && fb_banded_template_D(st->halfwidth) > 0; }
+
+// `st` describes the PROBABILITY-domain matrix (vit_analyze_structure_f32 on A; the band and the dense state are the same
+// whichever way round the matrix is stored): band + one dense state, every other entry exactly 0.  S <= 384 with d <= 14:
+// convolution kernel or general band kernel; up to S = 768 with d <= 56 (jdc, imm): convolution kernel or, when the band is
+// not scaled-Toeplitz, the dense FFMA kernel.
+bool fb_banded_supported(int S, const vit_structure* st) {
+  if (!st || st->kind != 1) return false;
+  if (st->background != 0.f) return false;
+  if (S < 2 || st->halfwidth < 0) return false;
+  if (st->dense_index < -1 || st->dense_index >= S) return false;
+  if (fb_banded_narrow(S, st)) return true;
+  return fb_conv_template_D(S, st->halfwidth) > 0 && fb_supported(S);
+}
+
 static size_t fb_banded_cnorm_bytes(int B, int T_max) { return align_up((size_t)(B > 0 ? B : 1) * T_max * sizeof(float), 256); }
-size_t fb_banded_workspace_bytes(int B, int T_max) { return fb_banded_cnorm_bytes(B, T_max) + fb_conv_params_bytes(); }
+// what the structured kernels keep at the END of the workspace (their normalisers and the parameter block): the front
+// belongs to the dense kernels, which may run as the fall-back in the same call
+size_t fb_banded_extra_bytes(int B, int T_max) { return fb_banded_cnorm_bytes(B, T_max) + fb_conv_params_bytes(); }
 
 int fb_banded_run(const float* A, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max, int S,
                   const vit_structure* st, void* workspace, size_t workspace_bytes, float* gamma, float* loglik,
                   cudaStream_t stream) {
   if (!fb_banded_supported(S, st)) return VIT_ERR_UNSUPPORTED_ALGO;
   if ((long long)B * T_max >= 0x7fffffffLL) return VIT_ERR_INVALID_ARGUMENT;   // (frame indices are int32 in the kernel)
-  if (workspace_bytes < fb_banded_workspace_bytes(B, T_max)) return VIT_ERR_WORKSPACE_TOO_SMALL;
+  const size_t extra = fb_banded_extra_bytes(B, T_max);
+  if (workspace_bytes < extra) return VIT_ERR_WORKSPACE_TOO_SMALL;
   if (B == 0) return VIT_OK;
-  float* cnorm = (float*)workspace;
-  void* conv_params = (char*)workspace + fb_banded_cnorm_bytes(B, T_max);     // its first word is the verdict
+  const size_t front = (workspace_bytes - extra) & ~(size_t)255;
+  float* cnorm = (float*)((char*)workspace + front);
+  void* conv_params = (char*)cnorm + fb_banded_cnorm_bytes(B, T_max);         // its first word is the verdict
+  const bool narrow = fb_banded_narrow(S, st);
+  if (!narrow && front < fb_workspace_bytes(B, T_max, S)) return VIT_ERR_WORKSPACE_TOO_SMALL;
   // frames past a clip's length carry gamma = 0
   if (lengths) VIT_CUDA_TRY(cudaMemsetAsync(gamma, 0, (size_t)B * T_max * S * sizeof(float), stream));
-  const int D = fb_banded_template_D(st->halfwidth);
-  // Scaled-Toeplitz check on the device, then BOTH kernel pairs: the convolution kernels return at once unless the
+  const int D = narrow ? fb_banded_template_D(st->halfwidth) : fb_conv_template_D(S, st->halfwidth);
+  // Scaled-Toeplitz check on the device, then BOTH kernel sets: the convolution kernels return at once unless the
   // check passed, the general kernels return at once if it did -- no round trip to the host.
   int rc = fb_conv_detect(A, S, st, D, conv_params, stream);
   if (rc != VIT_OK) return rc;
   rc = fb_conv_passes(D, conv_params, pi, lik, lengths, B, T_max, S, st->dense_index, gamma, cnorm, stream);
   if (rc != VIT_OK) return rc;
+  if (loglik) {
+    fb_loglik_kernel<<<(B + 3) / 4, 128, 0, stream>>>(cnorm, lengths, B, T_max, loglik, (const int*)conv_params, 1);
+    note_launch();
+    VIT_CUDA_TRY(cudaGetLastError());
+  }
+  if (!narrow)   // wide bands / 722 states that are not scaled-Toeplitz: the dense FFMA kernel (its own normalisers in the front)
+    return fb_run(A, pi, lik, lengths, B, T_max, S, workspace, front, gamma, loglik, nullptr, nullptr, stream,
+                  (const int*)conv_params);
   int num_sms = 148, dev = 0;
   VIT_CUDA_TRY(cudaGetDevice(&dev));
   VIT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -506,7 +532,7 @@ int fb_banded_run(const float* A, const float* pi, const float* lik, const int32
   note_launch(2);
   VIT_CUDA_TRY(cudaGetLastError());
   if (loglik) {
-    fb_loglik_kernel<<<(B + 3) / 4, 128, 0, stream>>>(cnorm, lengths, B, T_max, loglik);
+    fb_loglik_kernel<<<(B + 3) / 4, 128, 0, stream>>>(cnorm, lengths, B, T_max, loglik, (const int*)conv_params, 0);
     note_launch();
     VIT_CUDA_TRY(cudaGetLastError());
   }

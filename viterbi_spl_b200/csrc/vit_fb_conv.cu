@@ -33,7 +33,8 @@ constexpr int vMaxS = 32 * vNJ;            // 384
 constexpr int vDP = 16;                    // state i lives at float index i + vDP of a vector row
 constexpr int vRow = vMaxS + 2 * vDP;      // 416
 constexpr int vStages = 3;                 // input rows are fetched two steps ahead
-constexpr int vMaxTaps = 32;
+constexpr int vMaxTaps = 128;               // 2 * 56 + 1 taps of the widest band, rounded up
+constexpr int vMaxSW = 2 * vMaxS;          // the wide kernel: two blocks of 384 states per warp
 
 struct ConvParams {
   int flag;                                // 1: the matrix has the scaled-Toeplitz form, the convolution kernels run
@@ -41,12 +42,12 @@ struct ConvParams {
   float q_out;                             // A[u][j]: the dense state -> every band state
   float a_uu;
   float tap[vMaxTaps];                     // tap[x + Dt] = b[x], x = j - i, Dt = the kernel instance's half-width
-  float kappa[vMaxS];
+  float kappa[vMaxSW];
 };
 
 size_t fb_conv_params_bytes() { return align_up(sizeof(ConvParams), 256); }
 
-// one block of 384 threads; thread i checks source row i
+// one block of 384 threads; thread i checks source rows i and i + 384
 __global__ void fb_conv_detect_kernel(const float* __restrict__ A, int S, int jd, int d, int Dt, int enable,
                                       ConvParams* __restrict__ prm) {
   // d: the band's half-width; Dt >= d: the half-width of the kernel instance that will run (taps are stored for it)
@@ -61,7 +62,7 @@ __global__ void fb_conv_detect_kernel(const float* __restrict__ A, int S, int jd
       const int c = (S / 2 + k) % S;
       if (c - d >= 0 && c + d < S && (jd < c - d || jd > c + d)) istar = c;
     }
-    s_istar = (enable && S <= vMaxS && 2 * Dt + 1 <= vMaxTaps && d <= Dt) ? istar : -1;
+    s_istar = (enable && S <= vMaxSW && 2 * Dt + 1 <= vMaxTaps && d <= Dt) ? istar : -1;
     // the constants every dense-row / dense-column entry must equal
     const int i0 = jd == 0 ? 1 : 0;
     s_rq[0] = (jd >= 0 && S > 1) ? A[(size_t)i0 * S + jd] : 0.f;
@@ -80,29 +81,31 @@ __global__ void fb_conv_detect_kernel(const float* __restrict__ A, int S, int jd
   }
   __syncthreads();
   bool ok = true;
-  float kap = 0.f;
-  if (i < S && i != jd) {
-    float sa = 0.f, sb = 0.f;
-    for (int r = 0; r < W; ++r) {
-      const int j = i + r - d;
-      if (j >= 0 && j < S && j != jd) { sa += A[(size_t)i * S + j]; sb += s_b[r]; }
-    }
-    kap = sb > 0.f ? sa / sb : 0.f;
-    ok = kap > 0.f && kap < 1e30f;
-    for (int r = 0; r < W; ++r) {
-      const int j = i + r - d;
-      if (j >= 0 && j < S && j != jd) {
-        const float ref = kap * s_b[r];
-        ok = ok && fabsf(A[(size_t)i * S + j] - ref) <= 2e-6f * ref + 1e-37f;
+  for (int i2 = i; i2 < vMaxSW; i2 += vMaxS) {
+    float kap = 0.f;
+    if (i2 < S && i2 != jd) {
+      float sa = 0.f, sb = 0.f;
+      for (int r = 0; r < W; ++r) {
+        const int j = i2 + r - d;
+        if (j >= 0 && j < S && j != jd) { sa += A[(size_t)i2 * S + j]; sb += s_b[r]; }
+      }
+      kap = sb > 0.f ? sa / sb : 0.f;
+      ok = ok && kap > 0.f && kap < 1e30f;
+      for (int r = 0; r < W; ++r) {
+        const int j = i2 + r - d;
+        if (j >= 0 && j < S && j != jd) {
+          const float ref = kap * s_b[r];
+          ok = ok && fabsf(A[(size_t)i2 * S + j] - ref) <= 2e-6f * ref + 1e-37f;
+        }
+      }
+      if (jd >= 0) {
+        ok = ok && fabsf(A[(size_t)i2 * S + jd] - s_rq[0]) <= 2e-6f * s_rq[0];
+        ok = ok && fabsf(A[(size_t)jd * S + i2] - s_rq[1]) <= 2e-6f * s_rq[1];
       }
     }
-    if (jd >= 0) {
-      ok = ok && fabsf(A[(size_t)i * S + jd] - s_rq[0]) <= 2e-6f * s_rq[0];
-      ok = ok && fabsf(A[(size_t)jd * S + i] - s_rq[1]) <= 2e-6f * s_rq[1];
-    }
+    prm->kappa[i2] = kap;
   }
   const int all_ok = __syncthreads_and(ok ? 1 : 0);
-  if (i < vMaxS) prm->kappa[i] = (i < S && i != jd) ? kap : 0.f;
   if (i < vMaxTaps) {
     const int x = i - Dt;                                  // tap[x + Dt] = b[x]
     prm->tap[i] = (x >= -d && x <= d) ? s_b[x + d] : 0.f;
@@ -331,6 +334,213 @@ fb_conv_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict_
   }
 }
 
+// ---- wide bands / 722-state sets (jdc: +-40 of 721 bins; the imm HMM: +-56) ------------------------------------------
+// Same convolution, one warp per clip, but 2d + 1 = 81 .. 113 taps do not fit the register file and 722 states are 24 per
+// lane.  So: a lane owns TWO runs of 12 consecutive states, [12 l, 12 l + 12) and [384 + 12 l, 384 + 12 l + 12) -- both at
+// the 48-byte lane stride whose LDS.128 are conflict-free -- and sweeps them one after the other; the taps live in shared
+// memory and pass through a sliding window of 16 registers (one broadcast LDS.128 = 4 new taps per window float4, i.e. per
+// up to 48 FFMAs), the vector's window likewise slides by one float4 per iteration.  kappa sits in shared memory too.
+constexpr int wDPmax = 56;
+template <int D, bool BWD, int NF>
+__global__ void __launch_bounds__(32, 8)
+fb_convw_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict__ pi, const float* __restrict__ lik,
+                     const int32_t* __restrict__ lengths, int T_max, int S, int jd, float* __restrict__ gamma,
+                     float* __restrict__ cnorm) {
+  if (prm->flag == 0) return;
+  static_assert(D % 4 == 0 && D <= wDPmax, "wide instance");
+  constexpr int W = 2 * D + 1;
+  constexpr int NM = (vNJ + 2 * D) / 4;               // float4s of a run's window: inputs [run start - D, run start + 11 + D]
+  constexpr int KINDS = BWD ? 2 : 1;
+  constexpr int ROW = vMaxSW + 2 * D;                 // state i at float index i + D
+  constexpr int NG = D / 2 + 1;                       // tap groups of 4: tap rr in group rr >> 2; groups -1 and NG .. NG + 1 are 0
+  constexpr int NEL = vMaxSW / 32;                    // 24 element rows in the lane-contiguous layout
+  extern __shared__ __align__(16) float sm[];
+  float* s_row = sm;                                  // [2][ROW]
+  float* s_in = s_row + 2 * ROW;                      // [vStages][KINDS][vMaxSW]
+  float* s_out = s_in + vStages * KINDS * vMaxSW;     // [vMaxSW]
+  float* s_kap = s_out + vMaxSW;                      // [vMaxSW]
+  float* s_tap = s_kap + vMaxSW;                      // [(NG + 3) * 4]: group g at float4 index g + 1
+  __shared__ float s_ind[vStages][3];
+
+  const int lane = threadIdx.x;
+  const int b = blockIdx.x;
+  const int len = lengths ? lengths[b] : T_max;
+  if (len <= 0) return;
+  const float r_in = prm->r_in, q_out = prm->q_out, a_uu = prm->a_uu;
+  const bool has_d = jd >= 0;
+
+  for (int x = lane; x < 2 * ROW; x += 32) s_row[x] = 0.f;
+  for (int x = lane; x < vStages * KINDS * vMaxSW; x += 32) s_in[x] = 0.f;
+  for (int x = lane; x < vMaxSW; x += 32) s_kap[x] = prm->kappa[x];
+  for (int x = lane; x < (NG + 3) * 4; x += 32) {
+    const int rr = x - 4;                              // tap index (out - in) + D of this slot
+    s_tap[x] = (rr >= 0 && rr < W) ? prm->tap[BWD ? W - 1 - rr : rr] : 0.f;
+  }
+  __syncwarp();
+
+  const int Sv = has_d ? S - 1 : S;
+  auto elem_ok = [&](int n) {
+    if constexpr (NF >= 0) return n < NF || (n == NF && lane + 32 * NF < Sv);
+    else return lane + 32 * n < S && lane + 32 * n != jd;
+  };
+  constexpr int NROWS = NF >= 0 ? NF + 1 : NEL;
+  const long long dS = BWD ? -(long long)S : (long long)S;
+  const long long gamma_delta = reinterpret_cast<const char*>(gamma) - reinterpret_cast<const char*>(lik);
+  const float* pin = lik + ((size_t)b * T_max + (BWD ? len - 1 : 0)) * S + lane;
+  float* pout = gamma + ((size_t)b * T_max + (BWD ? len - 1 : 0)) * S + lane;
+  float* pc = cnorm + (size_t)b * T_max;
+
+  auto stage = [&](int it_f) {
+    if (it_f < len) {
+      const int sb = it_f % vStages;
+      float* dst = s_in + sb * KINDS * vMaxSW + lane;
+      const uint32_t d0 = smem_u32(dst), d1 = smem_u32(dst + (KINDS - 1) * vMaxSW);
+      const float* srca = reinterpret_cast<const float*>(reinterpret_cast<const char*>(pin) + gamma_delta);
+#pragma unroll
+      for (int n = 0; n < NROWS; ++n)
+        if (elem_ok(n)) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 128 * n), "l"(pin + 32 * n) : "memory");
+          if (BWD) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d1 + 128 * n), "l"(srca + 32 * n) : "memory");
+        }
+      if (BWD && lane == 1)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s_ind[sb][2])), "l"(pc + (len - 1 - it_f)) : "memory");
+      if (has_d && lane == 0) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s_ind[sb][0])), "l"(pin + jd) : "memory");
+        if (BWD) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s_ind[sb][1])), "l"(srca + jd) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    pin += dS;
+  };
+  stage(0);
+  stage(1);
+  stage(2);
+
+  float xd = 0.f, ss = 0.f, cprev = 1.f;
+
+  // acc[n] (+)= sum_in row[in] tap[(out - in) + D] for the run of 12 states that starts at state `run`
+  auto sweep = [&](const float* row, int run, float* acc) {
+    const float4* row4 = reinterpret_cast<const float4*>(row + run) + 3 * lane;     // window element 0 = state run + 12 l - D
+    const float4* tap4 = reinterpret_cast<const float4*>(s_tap) + 1;
+    float tq[4][4];                                    // taps of groups g, slot g & 3
+#pragma unroll
+    for (int g = D / 2 - 1 < -1 ? -1 : D / 2 - 1; g <= D / 2 + 2; ++g) {
+      if (g == D / 2 - 1) continue;                    // (loaded by iteration 0)
+      const float4 x = tap4[g];
+      tq[g & 3][0] = x.x; tq[g & 3][1] = x.y; tq[g & 3][2] = x.z; tq[g & 3][3] = x.w;
+    }
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      const float4 x = row4[m];
+      const float wv[4] = {x.x, x.y, x.z, x.w};
+      {
+        const int g = D / 2 - m - 1;                   // the lowest tap group this iteration needs
+        if (g >= -1) {
+          const float4 y = tap4[g];
+          tq[g & 3][0] = y.x; tq[g & 3][1] = y.y; tq[g & 3][2] = y.z; tq[g & 3][3] = y.w;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int n = 0; n < vNJ; ++n) {
+          const int rr = n - (4 * m + k) + 2 * D;      // in = run + 12 l + 4 m + k - D, out = run + 12 l + n
+          if (rr >= 0 && rr < W) acc[n] = fmaf(wv[k], tq[(rr >> 2) & 3][rr & 3], acc[n]);
+        }
+    }
+  };
+
+  for (int it = 0; it < len; ++it) {
+    const int t = BWD ? len - 1 - it : it;
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncwarp();
+    const int sb = it % vStages;
+    const float* in = s_in + sb * KINDS * vMaxSW;
+    const float ed = has_d ? s_ind[sb][0] : 0.f;
+    const float sband = vwarp_sum(ss);
+    const float* rowp = s_row + ((it & 1) ^ 1) * ROW;
+    float* rown = s_row + (it & 1) * ROW + D;
+    // per-step scalars
+    float inv = 0.f, invc = 0.f, invn = 0.f, add = 0.f, ct = 1.f;
+    const bool first = !BWD && it == 0, last = BWD && it == 0;
+    if constexpr (!BWD) {
+      const float tot = sband + xd;
+      if (lane == 0 && it > 0) pc[t - 1] = tot;
+      inv = vrcp_pos(tot);
+    } else {
+      ct = s_ind[sb][2];
+      invc = vrcp_pos(ct);
+      invn = vrcp_pos(cprev);
+      add = xd * r_in;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int run = vMaxS * h;
+      float acc[vNJ];
+      const float acc0 = BWD ? 0.f : xd * q_out;
+#pragma unroll
+      for (int n = 0; n < vNJ; ++n) acc[n] = acc0;
+      if (!first) sweep(rowp, run, acc);
+      float v[vNJ], o[vNJ];
+#pragma unroll
+      for (int m = 0; m < vNJ / 4; ++m) {
+        const float4 e4 = reinterpret_cast<const float4*>(in + run)[3 * lane + m];
+        const float4 k4 = reinterpret_cast<const float4*>(s_kap + run)[3 * lane + m];
+        const float e[4] = {e4.x, e4.y, e4.z, e4.w}, kp[4] = {k4.x, k4.y, k4.z, k4.w};
+        float al[4] = {0.f, 0.f, 0.f, 0.f};
+        if constexpr (BWD) {
+          const float4 a4 = reinterpret_cast<const float4*>(in + vMaxSW + run)[3 * lane + m];
+          al[0] = a4.x; al[1] = a4.y; al[2] = a4.z; al[3] = a4.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int n = 4 * m + k;
+          if constexpr (!BWD) {
+            const int j = run + vNJ * lane + n;
+            const float val = first ? (j < S ? pi[j] * e[k] : 0.f) : (acc[n] * inv) * e[k];
+            v[n] = val;
+            o[n] = val;
+          } else {
+            const float be = last ? 1.f : fmaf(kp[k], acc[n], add) * invn;
+            o[n] = (al[k] * invc) * be;
+            v[n] = e[k] * be;
+          }
+          s += v[n];
+        }
+        const float4 u = BWD ? make_float4(v[4 * m], v[4 * m + 1], v[4 * m + 2], v[4 * m + 3])
+                             : make_float4(v[4 * m] * kp[0], v[4 * m + 1] * kp[1], v[4 * m + 2] * kp[2], v[4 * m + 3] * kp[3]);
+        reinterpret_cast<float4*>(rown + run)[3 * lane + m] = u;
+        reinterpret_cast<float4*>(s_out + run)[3 * lane + m] = make_float4(o[4 * m], o[4 * m + 1], o[4 * m + 2], o[4 * m + 3]);
+      }
+    }
+    ss = s;
+    float xdn, out_d;
+    if constexpr (!BWD) {
+      xdn = has_d ? (first ? pi[jd] * ed : (fmaf(sband, r_in, xd * a_uu) * inv) * ed) : 0.f;
+      out_d = xdn;
+    } else {
+      const float bed = last ? 1.f : fmaf(sband, q_out, xd * a_uu) * invn;
+      const float ald = has_d ? s_ind[sb][1] : 0.f;
+      out_d = (ald * invc) * bed;
+      xdn = has_d ? ed * bed : 0.f;
+      cprev = ct;
+    }
+    xd = xdn;
+    __syncwarp();
+    stage(it + 3);
+#pragma unroll
+    for (int n = 0; n < NROWS; ++n)
+      if (elem_ok(n)) st_global_cs_f32(pout + 32 * n, s_out[lane + 32 * n]);
+    if (has_d && lane == 0) st_global_cs_f32(pout + jd, out_d);
+    pout += dS;
+  }
+  if (!BWD) {
+    const float sband = vwarp_sum(ss);
+    if (lane == 0) pc[len - 1] = sband + xd;
+  }
+}
+
 // vit_fb_banded.cu calls these
 int fb_conv_detect(const float* A, int S, const vit_structure* st, int Dt, void* params, cudaStream_t stream) {
   const char* e = getenv("VIT_FB_CONV");
@@ -341,26 +551,66 @@ int fb_conv_detect(const float* A, int S, const vit_structure* st, int Dt, void*
   return VIT_OK;
 }
 
+static int fb_conv_template_wide(int d) {
+  const int opts[] = {20, 28, 40, 56};
+  for (int o : opts) if (d <= o) return o;
+  return -1;
+}
+// the kernel instance's half-width for this shape (taps are stored for it), or -1
+int fb_conv_template_D(int S, int d) {
+  if (S <= vMaxS && d <= 14) {
+    const int opts[] = {4, 8, 12, 14};
+    for (int o : opts) if (d <= o) return o;
+  }
+  if (S <= vMaxSW) return fb_conv_template_wide(d);
+  return -1;
+}
+
 int fb_conv_passes(int D, const void* params, const float* pi, const float* lik, const int32_t* lengths, int B, int T_max,
                    int S, int jd, float* gamma, float* cnorm, cudaStream_t stream) {
-  const size_t smem_f = (size_t)(2 * vRow + vStages * 1 * vMaxS + vMaxS) * sizeof(float);
-  const size_t smem_b = (size_t)(2 * vRow + vStages * 2 * vMaxS + vMaxS) * sizeof(float);
-  // NF: the element-row specialisation (see the kernel).  Instances exist for the two layouts the reference's state sets
-  // have -- band states [0, Sv) with Sv in (288, 320] (dcnet: 320 bins) or (352, 384] (tonet / ftanet: 360) -- else generic.
+  const ConvParams* prm = (const ConvParams*)params;
+  // NF: the element-row specialisation (see the kernels).  Instances exist for the layouts the reference's state sets
+  // have -- band states [0, Sv) with Sv in (288, 320] (dcnet: 320 bins), (352, 384] (tonet / ftanet: 360), (704, 736]
+  // (jdc / imm: 721) -- else generic.
   const int Sv = jd >= 0 ? S - 1 : S;
   const bool tail_dense = jd < 0 || jd == S - 1;
   const int nf = (tail_dense && Sv > 0) ? (Sv - 1) / 32 : -1;
+  if (D > 14) {
+    // wide instance: two runs of 12 states per lane, taps and kappa in shared memory
+    const size_t fl = (size_t)2 * (vMaxSW + 2 * D) + vMaxSW + vMaxSW + (size_t)(D / 2 + 4) * 4;
+    const size_t smem_f = (fl + (size_t)vStages * 1 * vMaxSW) * sizeof(float);
+    const size_t smem_b = (fl + (size_t)vStages * 2 * vMaxSW) * sizeof(float);
+#define VIT_FBW_LAUNCH(DD, NFF)                                                                                       \
+  do {                                                                                                                \
+    fb_convw_pass_kernel<DD, false, NFF><<<B, 32, smem_f, stream>>>(prm, pi, lik, lengths, T_max, S, jd, gamma, cnorm); \
+    fb_convw_pass_kernel<DD, true, NFF><<<B, 32, smem_b, stream>>>(prm, pi, lik, lengths, T_max, S, jd, gamma, cnorm);  \
+  } while (0)
+#define VIT_FBW_CASE(DD)                                                                                              \
+  case DD:                                                                                                            \
+    if (nf == 22) VIT_FBW_LAUNCH(DD, 22);                                                                             \
+    else VIT_FBW_LAUNCH(DD, -1);                                                                                      \
+    break;
+    switch (D) {
+      VIT_FBW_CASE(20) VIT_FBW_CASE(28) VIT_FBW_CASE(40) VIT_FBW_CASE(56)
+      default: return VIT_ERR_UNSUPPORTED_ALGO;
+    }
+#undef VIT_FBW_CASE
+#undef VIT_FBW_LAUNCH
+    note_launch(2);
+    VIT_CUDA_TRY(cudaGetLastError());
+    return VIT_OK;
+  }
+  const size_t smem_f = (size_t)(2 * vRow + vStages * 1 * vMaxS + vMaxS) * sizeof(float);
+  const size_t smem_b = (size_t)(2 * vRow + vStages * 2 * vMaxS + vMaxS) * sizeof(float);
 #define VIT_FBC_LAUNCH(DD, NFF)                                                                                      \
   do {                                                                                                               \
-    fb_conv_pass_kernel<DD, false, NFF><<<B, 32, smem_f, stream>>>((const ConvParams*)params, pi, lik, lengths, T_max, S, \
-                                                                   jd, gamma, cnorm);                               \
-    fb_conv_pass_kernel<DD, true, NFF><<<B, 32, smem_b, stream>>>((const ConvParams*)params, pi, lik, lengths, T_max, S,  \
-                                                                  jd, gamma, cnorm);                                \
+    fb_conv_pass_kernel<DD, false, NFF><<<B, 32, smem_f, stream>>>(prm, pi, lik, lengths, T_max, S, jd, gamma, cnorm); \
+    fb_conv_pass_kernel<DD, true, NFF><<<B, 32, smem_b, stream>>>(prm, pi, lik, lengths, T_max, S, jd, gamma, cnorm);  \
   } while (0)
 #define VIT_FBC_CASE(DD)                                                                                             \
   case DD:                                                                                                           \
     if (nf == 11) VIT_FBC_LAUNCH(DD, 11);                                                                            \
-    else if (nf == 9) VIT_FBC_LAUNCH(DD, 9);                                                                       \
+    else if (nf == 9) VIT_FBC_LAUNCH(DD, 9);                                                                         \
     else VIT_FBC_LAUNCH(DD, -1);                                                                                     \
     break;
   switch (D) {

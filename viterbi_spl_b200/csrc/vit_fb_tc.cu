@@ -662,7 +662,7 @@ size_t fb_tc_workspace_bytes(int B, int T_max, int S) {
 
 // vit_fb.cu
 __global__ void fb_loglik_kernel(const float* __restrict__ cnorm, const int32_t* __restrict__ lengths, int B, int T_max,
-                                 float* __restrict__ loglik);
+                                 float* __restrict__ loglik, const int* __restrict__ flag, int want);
 
 static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int C, size_t smem, int grid, cudaStream_t stream) {
   *cfg = cudaLaunchConfig_t{};
@@ -734,7 +734,7 @@ int fb_tc_run(const float* A, const float* pi, const float* lik, const int32_t* 
   const int rc = launch_passes<16>(p, packed, pi, lik, lengths, B, T_max, S, gamma, cnorm, max_clusters, stream);
   if (rc != VIT_OK) return rc;
   if (loglik) {
-    fb_loglik_kernel<<<(B + 3) / 4, 128, 0, stream>>>(cnorm, lengths, B, T_max, loglik);
+    fb_loglik_kernel<<<(B + 3) / 4, 128, 0, stream>>>(cnorm, lengths, B, T_max, loglik, nullptr, 0);
     note_launch();
     VIT_CUDA_TRY(cudaGetLastError());
   }

@@ -50,9 +50,12 @@ class ForwardBackward:
 
     @property
     def structured(self):
-        """True when 'auto' takes the banded kernel for this matrix (unless VIT_FB_IMPL overrides it)."""
+        """True when 'auto' takes the structured kernels for this matrix (unless VIT_FB_IMPL overrides it): band + one
+        dense state with exact zeros elsewhere, S <= 384 with half-width <= 14 or S <= 768 with half-width <= 56."""
         st = self.structure
-        return bool(st.kind == 1 and st.background == 0.0 and st.halfwidth <= 14 and 2 <= self.S <= 384)
+        if not (st.kind == 1 and st.background == 0.0 and self.S >= 2):
+            return False
+        return (self.S <= 384 and st.halfwidth <= 14) or (self.S <= 768 and st.halfwidth <= 56)
 
     def run_device(self, lik, lengths=None, gamma=None, loglik=None):
         """lik: CUDA float32 [B, T, S] likelihoods (>= 0); lengths: CUDA int32 [B] or None.
