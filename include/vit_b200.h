@@ -185,12 +185,13 @@ int vit_forward_backward_f32(const float* d_A, const float* d_pi, const float* d
  *   VIT_FB_SIMT    dense FFMA kernel (any S the tensor-memory plan takes, e.g. 722)
  *   VIT_FB_BANDED  band + one dense state, every other entry exactly 0 -- what viterbi_transition_matrix.py builds
  *                  (dcnet/viterbi_transition_matrix.py:81-98): S (2d + 3) multiply-adds per frame instead of S^2, fp32.
- *                  `structure` = vit_analyze_structure_f32 of the HOST copy of d_A (kind 1, background 0, halfwidth
- *                  <= 14, S <= 384); VIT_ERR_UNSUPPORTED_ALGO otherwise.  When, in addition, the band is one tap vector
- *                  scaled per source row (A[i][j] = kappa_i b[j-i] within 2e-6 relative -- the rows of that recipe are
- *                  one jump histogram, normalised) and the dense row / column are constant, the band product runs as a
- *                  convolution, one warp per clip (checked on the device at every call; the general band kernel runs
- *                  otherwise; VIT_FB_CONV=0 in the environment switches the check off).
+ *                  `structure` = vit_analyze_structure_f32 of the HOST copy of d_A (kind 1, background 0; halfwidth
+ *                  <= 14 with S <= 384, or halfwidth <= 56 with S <= 768: the 722-state sets);
+ *                  VIT_ERR_UNSUPPORTED_ALGO otherwise.  When, in addition, the band is one tap vector scaled per source
+ *                  row (A[i][j] = kappa_i b[j-i] within 2e-6 relative -- the rows of that recipe are one jump histogram,
+ *                  normalised) and the dense row / column are constant, the band product runs as a convolution, one warp
+ *                  per clip (checked on the device at every call; otherwise the general band kernel runs for S <= 384
+ *                  and the dense FFMA kernel above it; VIT_FB_CONV=0 in the environment switches the check off).
  *   VIT_FB_AUTO    banded when `structure` allows it, else tc, else simt (what vit_forward_backward_f32 does with
  *                  structure = NULL).
  * The workspace size does not depend on the kernel. */
