@@ -76,3 +76,28 @@ def test_decode_rejects_bad_arguments_without_touching_the_gpu(cuda_lib):
     assert cuda_lib.vit_decode_f32(one, one, one, None, 1, 1, 65536, one, 1024, one, None, None) == -2
     assert cuda_lib.vit_decode_f32(one, one, one, None, 1, 1, 8, ctypes.c_void_p(257), 1 << 20, one, None, None) == -6
     assert cuda_lib.vit_decode_f32(one, one, one, None, 4, 100, 361, one, 16, one, None, None) == -3
+
+
+def test_forward_backward_ex_rejects_bad_arguments_without_touching_the_gpu(cuda_lib):
+    from viterbi_spl_b200 import _lib
+    one = ctypes.c_void_p(256)
+    opts = _lib.FbOpts()
+    opts.impl = _lib.FB_BANDED
+    st = _lib.Structure(1, 14, 360, 0.0, 0.0)
+    opts.structure = ctypes.pointer(st)
+    f = cuda_lib.vit_forward_backward_f32_ex
+    assert f(None, one, one, None, 1, 1, 361, one, 1 << 30, one, None, ctypes.byref(opts), None) == -1
+    assert f(one, one, one, None, 1, 0, 361, one, 1 << 30, one, None, ctypes.byref(opts), None) == -1
+    assert f(one, one, one, None, 1, 1, 70000, one, 1 << 30, one, None, ctypes.byref(opts), None) == -2
+    assert f(one, one, one, None, 4, 100, 361, ctypes.c_void_p(257), 1 << 30, one, None, ctypes.byref(opts), None) == -6
+    # the banded kernels need the structure: none / a log-domain background / a band wider than any instance -> unsupported
+    opts.structure = None
+    assert f(one, one, one, None, 4, 100, 361, one, 1 << 30, one, None, ctypes.byref(opts), None) == -4
+    for bad in (_lib.Structure(1, 14, 360, -87.3, 0.0), _lib.Structure(0, 14, 360, 0.0, 0.0), _lib.Structure(1, 57, 721, 0.0, 0.0)):
+        opts.structure = ctypes.pointer(bad)
+        S = 722 if bad.halfwidth > 14 else 361
+        assert f(one, one, one, None, 4, 100, S, one, 1 << 30, one, None, ctypes.byref(opts), None) == -4
+    # the workspace covers the dense kernels' needs plus the structured kernels' normalisers and parameter block
+    n = ctypes.c_size_t(0)
+    assert cuda_lib.vit_fb_workspace_bytes(64, 100, 361, ctypes.byref(n)) == 0
+    assert n.value >= 64 * 100 * 4 * 2
