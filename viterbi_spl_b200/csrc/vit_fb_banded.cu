@@ -408,7 +408,7 @@ fb_banded_pass_kernel(const float* __restrict__ A, const float* __restrict__ pi,
     __syncthreads();
     if (tid < fMB) {
       const int b = seq0 + tid;
-      s_len[tid] = (tid < q && b < B) ? (lengths ? lengths[b] : T_max) : 0;
+      s_len[tid] = (tid < q && b < B) ? min(lengths ? lengths[b] : T_max, T_max) : 0;
     }
     // (re-)arm the vector rows and the partial sums: pads, out-of-range states and the dense state's slot hold 0
     for (int x = tid; x < fCS * 2 * fCPT * fRowLen; x += fThreads) (&s_v[0][0][0][0])[x] = 0.f;

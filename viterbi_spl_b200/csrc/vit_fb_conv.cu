@@ -154,7 +154,7 @@ fb_conv_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict_
 
   const int lane = threadIdx.x;
   const int b = blockIdx.x;
-  const int len = lengths ? lengths[b] : T_max;
+  const int len = min(lengths ? lengths[b] : T_max, T_max);    // (a length past T_max would walk off the clip's rows)
   if (len <= 0) return;
   const int j0 = vNJ * lane;
 
@@ -364,7 +364,7 @@ fb_convw_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict
 
   const int lane = threadIdx.x;
   const int b = blockIdx.x;
-  const int len = lengths ? lengths[b] : T_max;
+  const int len = min(lengths ? lengths[b] : T_max, T_max);    // (a length past T_max would walk off the clip's rows)
   if (len <= 0) return;
   const float r_in = prm->r_in, q_out = prm->q_out, a_uu = prm->a_uu;
   const bool has_d = jd >= 0;
