@@ -61,19 +61,37 @@ def stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source into one shared library; returns its path."""
+    """Compile every CUDA source (one nvcc per file, in parallel) and link them into one shared library; returns its
+    path."""
     if not force and not stale():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + ['-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
     env = dict(os.environ)
     env.pop('CC', None)   # the image exports a wrapper CC that nvcc must not pick up as host compiler
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    if res.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr)
+    compile_flags = [f for f in NVCC_FLAGS if f != '-shared']
+    logs = []
+    with tempfile.TemporaryDirectory(prefix='vit_build_') as tmp:
+        def compile_one(src):
+            obj = os.path.join(tmp, src.replace('.cu', '.o'))
+            cmd = [nvcc()] + compile_flags + ['-c', '-o', obj, os.path.join(CSRC, src)]
+            res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+            if res.returncode != 0:
+                raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr)
+            return obj, res.stdout + res.stderr
+        with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+            results = list(pool.map(compile_one, SOURCES))
+        objs = [o for o, _ in results]
+        logs = [l for _, l in results]
+        cmd = [nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '--compiler-options', '-fPIC', '-o', LIB] + objs
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if res.returncode != 0:
+            raise RuntimeError('nvcc link failed:\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr)
+        logs.append(res.stdout + res.stderr)
     if verbose:
-        print(res.stdout + res.stderr)
+        print(''.join(logs))
     with open(os.path.join(HERE, 'build_ptxas.log'), 'w') as fh:
-        fh.write(res.stdout + res.stderr)
+        fh.write(''.join(logs))
     return LIB
 
 
