@@ -424,8 +424,7 @@ fb_convw_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict
     const float4* tap4 = reinterpret_cast<const float4*>(s_tap) + 1;
     float tq[4][4];                                    // taps of groups g, slot g & 3
 #pragma unroll
-    for (int g = D / 2 - 1 < -1 ? -1 : D / 2 - 1; g <= D / 2 + 2; ++g) {
-      if (g == D / 2 - 1) continue;                    // (loaded by iteration 0)
+    for (int g = D / 2; g <= D / 2 + 2; ++g) {         // iteration m needs groups D/2 - m - 1 .. D/2 - m + 2 and loads the lowest
       const float4 x = tap4[g];
       tq[g & 3][0] = x.x; tq[g & 3][1] = x.y; tq[g & 3][2] = x.z; tq[g & 3][3] = x.w;
     }
