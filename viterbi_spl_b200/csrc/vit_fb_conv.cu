@@ -146,6 +146,7 @@ fb_conv_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict_
   constexpr int U0 = vDP - D;                         // row offset (relative to 12 lane) of the first window element
   constexpr int M0 = U0 / 4, M1 = (U0 + vNJ - 1 + 2 * D) / 4;    // float4s of a lane's window: [M0, M1]
   constexpr int KINDS = BWD ? 2 : 1;
+  constexpr int PFL = 2;                              // L2 prefetches per lane for 4 rows of <= 384 floats
   extern __shared__ __align__(16) float sm[];
   float* s_row = sm;                                  // [2][vRow]: the vector the sweep reads (forward: alpha~ kappa, backward: w)
   float* s_in = sm + 2 * vRow;                        // [vStages][KINDS][vMaxS]: b_t (and alpha~_t) rows, fetched by cp.async
@@ -203,6 +204,23 @@ fb_conv_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict_
       if (has_d && lane == 0) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s_ind[sb][0])), "l"(pin + jd) : "memory");
         if (BWD) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s_ind[sb][1])), "l"(srca + jd) : "memory");
+      }
+    }
+    // HBM locality: the rows of a clip are one sequential stream, but a row is only 1.4 - 2.9 KB and thousands of clips
+    // advance in lock step, so row-sized requests reach DRAM as scattered page-sized pieces (ncu: ~64 % of the copy
+    // bandwidth at every batch size).  Every 4th step the warp pulls the NEXT FOUR rows of its stream (one contiguous
+    // piece of 5.8 - 11.5 KB) into L2; the row-sized cp.asyncs then hit L2.
+    if ((it_f & 3) == 0 && it_f + 4 < len) {
+      const long long first = BWD ? 7 * dS : 4 * dS;        // lowest address of rows it_f + 4 .. it_f + 7 of the stream
+      const char* base = reinterpret_cast<const char*>(pin - lane + first);
+      const int nbytes = 4 * S * 4;
+#pragma unroll
+      for (int k = 0; k < PFL; ++k) {
+        const int off = (lane + 32 * k) * 128;
+        if (off < nbytes) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+          if (BWD) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + gamma_delta + off));
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -272,13 +290,16 @@ fb_conv_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict_
     const int t = BWD ? len - 1 - it : it;
     float e[vNJ], ed;
     const float* in = step_inputs(it, e, ed);
-    const float sband = vwarp_sum(ss);                     // sum over the band states of the previous step's vector
-    // the band: acc[out] = sum_in row[in] tap[(out - in) + D]  (forward: on top of the dense state's contribution)
+    // the band: acc[out] = sum_in row[in] tap[(out - in) + D]  (forward: on top of the dense state's contribution).
+    // The warp sum of the previous step's vector (5 dependent shuffles: ~150 clocks of latency, a third of the kernel's
+    // stall samples when it sat in front of the sweep) is issued ONE ROUND PER WINDOW FLOAT4 inside the sweep: each
+    // round carries a data dependency on accumulators of that iteration, so ptxas cannot hoist the chain back to the top.
     float acc[vNJ];
     const float acc0 = BWD ? 0.f : xd * q_out;
 #pragma unroll
     for (int n = 0; n < vNJ; ++n) acc[n] = acc0;
     const float4* row4 = reinterpret_cast<const float4*>(s_row + ((it & 1) ^ 1) * vRow) + 3 * lane;
+    float sband = ss;
 #pragma unroll
     for (int m = M0; m <= M1; ++m) {
       const float4 x = row4[m];
@@ -290,7 +311,16 @@ fb_conv_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict_
           const int rr = n - (4 * m + k) + vDP + D;        // in = 12 lane + 4 m + k - vDP, out = 12 lane + n
           if (rr >= 0 && rr < W) acc[n] = fmaf(wv[k], tap[rr], acc[n]);
         }
+      if (m - M0 >= 1 && m - M0 <= 5) {
+        // (a REAL data dependency on this iteration's accumulators -- an empty asm leaves no trace in the PTX and ptxas
+        // hoisted the whole chain back to the loop top; 0 * acc is not foldable under IEEE rules.  The result is only
+        // perturbed if an accumulator is inf / NaN, i.e. if the inputs were not finite.)
+        sband = fmaf(acc[(5 * (m - M0)) % vNJ], 0.f, sband);
+        sband += __shfl_xor_sync(0xffffffffu, sband, 32 >> (m - M0));
+      }
     }
+#pragma unroll
+    for (int r = M1 - M0 + 1; r <= 5; ++r) sband += __shfl_xor_sync(0xffffffffu, sband, 32 >> r);   // (narrow windows)
     float v[vNJ], o[vNJ], xdn, out_d;
     if constexpr (!BWD) {
       // alpha~_t = ((alpha~_{t-1} kappa) * b + alpha~_{t-1}[u] q) / c_{t-1} * b_t ;  c_{t-1} = band sum + dense element
@@ -354,6 +384,7 @@ fb_convw_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict
   constexpr int ROW = vMaxSW + 2 * D;                 // state i at float index i + D
   constexpr int NG = D / 2 + 1;                       // tap groups of 4: tap rr in group rr >> 2; groups -1 and NG .. NG + 1 are 0
   constexpr int NEL = vMaxSW / 32;                    // 24 element rows in the lane-contiguous layout
+  constexpr int PFL = 3;                              // L2 prefetches per lane for 4 rows of <= 768 floats
   extern __shared__ __align__(16) float sm[];
   float* s_row = sm;                                  // [2][ROW]
   float* s_in = s_row + 2 * ROW;                      // [vStages][KINDS][vMaxSW]
@@ -409,6 +440,23 @@ fb_convw_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict
         if (BWD) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s_ind[sb][1])), "l"(srca + jd) : "memory");
       }
     }
+    // HBM locality: the rows of a clip are one sequential stream, but a row is only 1.4 - 2.9 KB and thousands of clips
+    // advance in lock step, so row-sized requests reach DRAM as scattered page-sized pieces (ncu: ~64 % of the copy
+    // bandwidth at every batch size).  Every 4th step the warp pulls the NEXT FOUR rows of its stream (one contiguous
+    // piece of 5.8 - 11.5 KB) into L2; the row-sized cp.asyncs then hit L2.
+    if ((it_f & 3) == 0 && it_f + 4 < len) {
+      const long long first = BWD ? 7 * dS : 4 * dS;        // lowest address of rows it_f + 4 .. it_f + 7 of the stream
+      const char* base = reinterpret_cast<const char*>(pin - lane + first);
+      const int nbytes = 4 * S * 4;
+#pragma unroll
+      for (int k = 0; k < PFL; ++k) {
+        const int off = (lane + 32 * k) * 128;
+        if (off < nbytes) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+          if (BWD) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + gamma_delta + off));
+        }
+      }
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
     pin += dS;
   };
@@ -456,7 +504,8 @@ fb_convw_pass_kernel(const ConvParams* __restrict__ prm, const float* __restrict
     const int sb = it % vStages;
     const float* in = s_in + sb * KINDS * vMaxSW;
     const float ed = has_d ? s_ind[sb][0] : 0.f;
-    const float sband = vwarp_sum(ss);
+    const float sband = vwarp_sum(ss);     // (needed by the per-step scalars below; the two sweeps that follow are long enough
+                                           // for the other clips of the scheduler to cover this chain)
     const float* rowp = s_row + ((it & 1) ^ 1) * ROW;
     float* rown = s_row + (it & 1) * ROW + D;
     // per-step scalars
