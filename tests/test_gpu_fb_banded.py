@@ -303,3 +303,52 @@ def test_c_abi_directly(cuda_lib):
     opts.structure = ctypes.pointer(st2)
     assert cuda_lib.vit_forward_backward_f32_ex(p(dA), p(dpi), p(lik), None, B, T, S, p(ws), n.value, p(gamma), p(ll),
                                                 ctypes.byref(opts), None) == -4
+
+
+@pytest.mark.parametrize('case', ['conv_narrow', 'conv_wide', 'general', 'wide_fallback'])
+def test_no_write_outside_gamma_loglik_and_workspace(cuda_lib, case):
+    """compute-sanitizer is not available on the pool: canaries either side of every output buffer instead.  gamma, log L
+    and the workspace are carved out of larger allocations filled with a sentinel; after the call the guards are intact."""
+    from viterbi_spl_b200 import _lib
+    rng = np.random.default_rng(31)
+    if case == 'conv_narrow':
+        A, pi = [x.astype(np.float32) for x in hmm_params.synthetic_hmm('tonet')]
+    elif case == 'conv_wide':
+        A, pi = [x.astype(np.float32) for x in hmm_params.synthetic_hmm('jdc')]
+    elif case == 'general':
+        A, pi = banded_hmm(361, 14, 360, rng)
+    else:
+        A, pi = banded_hmm(722, 30, 721, rng)
+    S = len(pi)
+    B, T = 7, 9
+    st = _lib.analyze_structure(A)
+    assert st.kind == 1 and st.background == 0.0
+    lik_h = np.exp(rng.standard_normal((B, T, S))).astype(np.float32)
+    L_h = np.asarray([T, 1, 0, 5, T, 2, 8], np.int32)
+    G = 4096
+    SENT = 12345.5
+    n = ctypes.c_size_t(0)
+    assert cuda_lib.vit_fb_workspace_bytes(B, T, S, ctypes.byref(n)) == 0
+    ws_bytes = (n.value + 255) // 256 * 256
+    big_g = torch.full((G + B * T * S + G,), SENT, device='cuda')
+    big_l = torch.full((G + B + G,), SENT, device='cuda')
+    big_w = torch.full((1024 + ws_bytes // 4 + G,), SENT, device='cuda')          # the workspace must be 256-byte aligned
+    w_off = (-(big_w.data_ptr() + 1024 * 4) % 256) // 4 + 1024
+    lik, L = torch.as_tensor(lik_h).cuda(), torch.as_tensor(L_h).cuda()
+    dA, dpi = torch.as_tensor(A).cuda(), torch.as_tensor(pi).cuda()
+    opts = _lib.FbOpts()
+    opts.impl = _lib.FB_BANDED
+    opts.structure = ctypes.pointer(st)
+    vp = ctypes.c_void_p
+    rc = cuda_lib.vit_forward_backward_f32_ex(vp(dA.data_ptr()), vp(dpi.data_ptr()), vp(lik.data_ptr()), vp(L.data_ptr()), B, T, S,
+                                               vp(big_w.data_ptr() + 4 * w_off), ws_bytes, vp(big_g.data_ptr() + 4 * G),
+                                               vp(big_l.data_ptr() + 4 * G), ctypes.byref(opts), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert bool((big_g[:G] == SENT).all()) and bool((big_g[G + B * T * S:] == SENT).all())
+    assert bool((big_l[:G] == SENT).all()) and bool((big_l[G + B:] == SENT).all())
+    assert bool((big_w[:w_off] == SENT).all()) and bool((big_w[w_off + ws_bytes // 4:] == SENT).all())
+    g = big_g[G:G + B * T * S].reshape(B, T, S).cpu().numpy()
+    want_g, want_ll = fb_oracle.forward_backward_batch_np(A, pi, lik_h, L_h)
+    assert np.abs(g - want_g).max() <= GAMMA_ATOL
+    assert np.allclose(big_l[G:G + B].cpu().numpy(), want_ll, rtol=LOGLIK_RTOL, atol=1e-5)
