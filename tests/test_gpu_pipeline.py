@@ -267,3 +267,26 @@ def test_melody_stats_softmax_layout_and_pipeline_evaluate(pl):
     assert np.allclose(est[0].cpu().numpy(), want, rtol=1e-5, atol=1e-5)
     got = dict(zip(pl.COUNTER_NAMES, counters[0].tolist()))
     assert all(abs(got[k] - c[k]) <= 1 for k in pl.COUNTER_NAMES), (got, c)
+
+
+@pytest.mark.parametrize('model,scaled', [('softmax', False), ('softmax', True), ('shaun', False)])
+def test_pipeline_posteriors_match_the_float64_oracle_on_the_emission_likelihoods(pl, model, scaled):
+    """logits -> observation_probs_fn likelihoods (GPU) -> forward-backward (GPU; the convolution kernels for this matrix)
+    against the float64 oracle run on the same likelihoods.  Parity unpinned: the reference has no forward-backward."""
+    from oracle import fb_oracle
+    A, pi = hmm_params.synthetic_hmm('tonet')
+    S = len(pi)
+    rng = np.random.default_rng(17)
+    B, T = 5, 60
+    n_in = S if model == 'softmax' else S - 1
+    logits = (2.0 * rng.standard_normal((B, T, n_in))).astype(np.float32)
+    L = np.asarray([T, 1, 0, 33, T], np.int32)
+    mp = pl.MelodyPipeline(A, pi, model=model, scaled=scaled)
+    d_logits = torch.as_tensor(logits).cuda()
+    lik = mp.emissions(d_logits, out_log=False).cpu().numpy()
+    gamma, ll = mp.posteriors(logits, L)
+    want_g, want_ll = fb_oracle.forward_backward_batch_np(A.astype(np.float32), pi.astype(np.float32), lik, L)
+    assert np.abs(gamma.cpu().numpy() - want_g).max() <= 1e-4
+    assert np.allclose(ll.cpu().numpy(), want_ll, rtol=1e-5, atol=1e-5)
+    g1, l1 = mp.posteriors(logits[0])                                 # a single recording [T, *]
+    assert g1.shape == (T, S) and np.abs(g1.cpu().numpy() - want_g[0]).max() <= 1e-4

@@ -108,6 +108,9 @@ class MelodyPipeline:
         self.prior = None
         if self.model == SOFTMAX and scaled:
             self.prior = torch.as_tensor(np.roll(np.asarray(ini_probs, np.float32), 1).copy()).to(self.device)
+        self._A = np.asarray(transition_matrix, np.float32)
+        self._pi = np.asarray(ini_probs, np.float32)
+        self._fb = None
 
     def emissions(self, logits, out_log=True):
         return emissions_device(logits, self.n_bins, self.model, self.prior, self.spw, self.threshold, out_log)
@@ -122,6 +125,25 @@ class MelodyPipeline:
         states, _ = self.decoder.decode_device(E, lengths)
         voiced, bins = voiced_bins_device(states, self.n_bins)
         return (voiced[0], bins[0]) if squeeze else (voiced, bins)
+
+    def posteriors(self, logits, lengths=None):
+        """logits [B, T, *] -> (gamma [B, T, n_bins + 1] posterior state marginals, unvoiced last; log L [B]): the emission
+        LIKELIHOODS of observation_probs_fn (probability domain, what dcnet/softmax_viterbi.py:2530-2579 returns) go straight
+        into the scaled forward-backward pass on the same transition matrix and initial distribution -- the sum-product
+        counterpart of __call__ (the reference only has the max-product decode; semantics: oracle/fb_oracle.py)."""
+        from .posterior import ForwardBackward
+        logits = torch.as_tensor(logits)
+        squeeze = logits.ndim == 2
+        if squeeze:
+            logits = logits[None]
+        logits = logits.to(self.device, torch.float32).contiguous()
+        if self._fb is None:
+            self._fb = ForwardBackward(self._A, self._pi, device=self.device)
+        if lengths is not None and not (torch.is_tensor(lengths) and lengths.is_cuda):
+            lengths = torch.as_tensor(checked_lengths(np.asarray(lengths), logits.shape[0], logits.shape[1])).to(self.device)
+        lik = self.emissions(logits, out_log=False)
+        gamma, ll = self._fb.run_device(lik, lengths)
+        return (gamma[0], ll[0]) if squeeze else (gamma, ll)
 
     def evaluate(self, logits, ref_notes, lengths=None, note_min=23.6, note_step=0.2):
         """logits [B, T, *] + reference notes [B, T] -> (voiced, bins, est_notes_with_voicing_info, counters [B, 9]):
