@@ -28,8 +28,19 @@ for model, scaled in (('softmax', True), ('shaun', False)):
     for _ in range(3):
         v, b = mp(logits)
     e1.record(); torch.cuda.synchronize()
-    out[model] = {'emissions_ms': ms, 'emissions_GBps': bytes_ / (ms * 1e-3) / 1e9,
-                  'chain_ms': e0.elapsed_time(e1) / 3, 'chain_frames_per_s': B * T / (e0.elapsed_time(e1) / 3 * 1e-3),
+    chain_ms = e0.elapsed_time(e1) / 3
+    del v, b
+    mp.posteriors(logits)                       # logits -> likelihoods -> forward-backward posteriors
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(3):
+        gam, ll = mp.posteriors(logits)
+    e1.record(); torch.cuda.synchronize()
+    post_ms = e0.elapsed_time(e1) / 3
+    del gam, ll
+    v, b = mp(logits)
+    out[model] = {'posterior_chain_ms': post_ms, 'posterior_chain_frames_per_s': B * T / (post_ms * 1e-3),
+                  'emissions_ms': ms, 'emissions_GBps': bytes_ / (ms * 1e-3) / 1e9,
+                  'chain_ms': chain_ms, 'chain_frames_per_s': B * T / (chain_ms * 1e-3),
                   'voiced_fraction': float(v.float().mean())}
     del mp, logits, v, b
     torch.cuda.empty_cache()
